@@ -1,0 +1,156 @@
+/*
+ * smesh.h -- C ABI of libsmesh_b200.so: the B200 (sm_100a) implementation of the two semantic-meshes hot paths.
+ *
+ * This is the drop-in boundary. The reference exposes these paths through two Boost.Python modules
+ * (python/semantic_meshes/src/Render.cu, python/semantic_meshes/src/Fusion.cu); every entry point below names the
+ * reference interface it replaces (paths relative to the reference checkout; tt/ = extern/template-tensors/include/
+ * template_tensors/). INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns every buffer (the Python layer holds them as torch tensors); the library keeps no state between
+ *     calls except the per-thread error string, so it is safe to use from several host threads / streams;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and never synchronises the device;
+ *   - return value 0 = success; anything else is an smesh_status and smesh_last_error() describes it
+ *     (SMESH_ERR_INVALID_ARGUMENT maps to the reference's std::invalid_argument -> Python ValueError);
+ *   - image layout is the reference's: (W, H[, C]) row-major, pixel (x, y) at x*H + y
+ *     (python/semantic_meshes/include/Renderer.h:29).
+ */
+#ifndef SMESH_H
+#define SMESH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum
+{
+  SMESH_OK = 0,
+  SMESH_ERR_INVALID_ARGUMENT = 1, /* std::invalid_argument in the reference (Mesh.h:68-74, Fusion.cu:122-125) */
+  SMESH_ERR_CUDA = 2,             /* a CUDA runtime call or kernel launch failed */
+  SMESH_ERR_UNSUPPORTED = 3       /* shape outside what the kernels support (see each function) */
+} smesh_status;
+
+/* Aggregator kinds; names and arithmetic of python/semantic_meshes/src/Fusion.cu:46-92. */
+typedef enum
+{
+  SMESH_KIND_SUM = 0,
+  SMESH_KIND_SUMMAX = 1,
+  SMESH_KIND_MUL = 2
+} smesh_kind;
+
+/* Element types accepted for primitive-index images (python/semantic_meshes/include/Common.h:5-12). */
+typedef enum
+{
+  SMESH_ID_U32 = 0,
+  SMESH_ID_I32 = 1,
+  SMESH_ID_U64 = 2,
+  SMESH_ID_I64 = 3
+} smesh_id_dtype;
+
+/* Last error message of the calling host thread ("" if none). */
+const char* smesh_last_error(void);
+
+/* Library / build identification, e.g. "smesh_b200 0.1 sm_100a". */
+const char* smesh_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Rasterizer: replaces Renderer<T>::render (python/semantic_meshes/include/Renderer.h:25-43) ->
+ * TriangleRenderer::render (include/semantic_meshes/render/TriangleRenderer.h:63-89) ->
+ * kernel_DeviceMutexRasterizer_nthreadsperprimitive (tt/geometry/render/DeviceMutexRasterizer.h:14-57) +
+ * Triangle::{precompute,intersect,rasterize} (tt/geometry/render/primitives/Triangle.h:47-164).
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Bytes of device scratch smesh_raster_render needs for a mesh of V vertices / F triangles at resolution W x H
+ * (camera-space vertex cache, per-view ray tables, packed 64-bit depth|index buffer, large-triangle queue). */
+int smesh_raster_workspace_bytes(int64_t V, int64_t F, int W, int H, size_t* bytes_host);
+
+/*
+ * Render one view: per pixel the index of the nearest hit triangle and its camera-space depth z.
+ *   verts   float32[V][3], faces int32[F][3]      (what TriangleRenderer's ctor uploads, TriangleRenderer.h:30-39)
+ *   R_host  float[9] row-major rotation, t_host float[3]   (Camera::extr, include/semantic_meshes/render/Camera.h:12)
+ *   f_host  double[2] focal lengths, c_host double[2] principal point (Camera::intr; the Python Camera rounds its
+ *           inputs to float first and then widens, python/semantic_meshes/include/Camera.h:19-54 - the caller does it)
+ *   W, H    Camera::resolution (1 <= W, H <= 65536)
+ *   idx_out uint32[W][H] (0xFFFFFFFF where nothing is hit), depth_out float32[W][H] (+inf where nothing is hit)
+ * Results are bit-identical to the reference kernel as compiled by nvcc 12.9 for sm_100a, with the one documented
+ * strengthening that exact depth ties go to the lowest triangle index (the reference is order-dependent there).
+ */
+int smesh_raster_render(const float* verts, int64_t V, const int32_t* faces, int64_t F, const float* R_host,
+                        const float* t_host, const double* f_host, const double* c_host, int W, int H, void* workspace,
+                        size_t workspace_bytes, uint32_t* idx_out, float* depth_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Label fusion: replaces ModelAggregator::{add1,add2,get,reset} (python/semantic_meshes/include/Fusion.h:42-76) ->
+ * semantic_meshes::ModelAggregator::{add,get,reset} (include/semantic_meshes/fusion/Mesh.h:57-133) with the chains
+ * of python/semantic_meshes/src/Fusion.cu:46-92.
+ *
+ * Accumulator: float32[P][Cpad] with Cpad = smesh_fuse_padded_classes(C) (rows padded to 16 bytes so a row is
+ * updated with 128-bit reductions); padding columns stay 0. For SMESH_KIND_MUL it holds -log p (tt/numeric/LogProb.h).
+ * reset() of the reference (Mesh.h:119-122) = zero-fill of this buffer by the caller.
+ * ------------------------------------------------------------------------------------------------------------- */
+
+int smesh_fuse_padded_classes(int C);
+
+/*
+ * One view into the accumulator = ModelAggregator::add (Mesh.h:65-107). Launches: per-face pixel count (Mesh.h:90-93),
+ * the gated, weighted scatter (Mesh.h:94-106), and the reset of the touched counters.
+ *
+ * Pixels are addressed by a flat index i = outer*n_inner + inner (n_pix = n_outer*n_inner); the caller picks
+ * outer/inner so that the probability image is contiguous in that order:
+ *   probs    float32[n_pix][C]  (16-byte aligned; class stride 1)
+ *   ids      element (outer, inner) at ids[outer*ids_stride_outer + inner*ids_stride_inner] (strides in elements),
+ *            type id_dtype; a pixel is background unless 0 <= id < P (Mesh.h:95)
+ *   weights  NULL (= 1.0f everywhere, Mesh.h:109-117) or float32, element (outer, inner) at
+ *            weights[outer*w_stride_outer + inner*w_stride_inner]
+ *   counts   uint32[P] scratch, must be all-zero on entry, is all-zero again on completion
+ *   ids32    uint32[n_pix] scratch (flat-order copy of the ids, 0xFFFFFFFF for background)
+ *   acc      float32[P][Cpad]
+ *   iew      images_equal_weight (Mesh.h:57,102)
+ * SMESH_ERR_UNSUPPORTED if C > 4096 or P >= 2^32 - 1.
+ */
+int smesh_fuse_add(int kind, const void* ids, int id_dtype, int64_t ids_stride_outer, int64_t ids_stride_inner,
+                   const float* probs, const float* weights, int64_t w_stride_outer, int64_t w_stride_inner,
+                   int64_t n_outer, int64_t n_inner, int C, int64_t P, float iew, uint32_t* counts, uint32_t* ids32,
+                   float* acc, void* stream);
+
+/*
+ * The three stages of smesh_fuse_add as separate calls (a caller that adds the same index image with several
+ * predictions can count once; bench.py times the scatter stage alone with them). Pixels in flat order:
+ *   smesh_fuse_count    per-face pixel count (Mesh.h:90-93) of ids (any id_dtype, strided) into counts[P] (+=, so counts
+ *                       must be zero on entry); ids32_out (may be NULL) receives the flat uint32 copy, background
+ *                       and out-of-range ids as 0xFFFFFFFF
+ *   smesh_fuse_scatter  gate + weight + accumulate (Mesh.h:94-106) from flat uint32 ids (anything >= P is background),
+ *                       flat probs [n_pix][C], flat weights (NULL = 1) and the counts of the same view
+ *   smesh_fuse_clear    counts[id] = 0 for every id < P in ids32
+ */
+int smesh_fuse_count(const void* ids, int id_dtype, int64_t ids_stride_outer, int64_t ids_stride_inner, int64_t n_outer,
+                     int64_t n_inner, int64_t P, uint32_t* counts, uint32_t* ids32_out, void* stream);
+int smesh_fuse_scatter(int kind, const uint32_t* ids32, const float* probs, const float* weights, int64_t n_pix, int C,
+                       int64_t P, float iew, const uint32_t* counts, float* acc, void* stream);
+int smesh_fuse_clear(const uint32_t* ids32, int64_t n_pix, int64_t P, uint32_t* counts, void* stream);
+
+/*
+ * A batch of B views with identical shapes, view b at ids + b*ids_stride_view (elements), probs + b*probs_stride_view
+ * (floats), weights + b*w_stride_view (floats, if weights != NULL). Equivalent to B calls of smesh_fuse_add in order.
+ */
+int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id_dtype, int64_t ids_stride_view,
+                         int64_t ids_stride_outer, int64_t ids_stride_inner, const float* probs,
+                         int64_t probs_stride_view, const float* weights, int64_t w_stride_view, int64_t w_stride_outer,
+                         int64_t w_stride_inner, int64_t n_outer, int64_t n_inner, int C, int64_t P, float iew,
+                         uint32_t* counts, uint32_t* ids32, float* acc, void* stream);
+
+/*
+ * ModelAggregator::get (Fusion.h:72-76): out float32[P][C] = per-face class distribution: the accumulator row
+ * (mul: exp(-(acc - min acc)), Fusion.h:96-104), L1-normalised, NaN/Inf -> 0 (Fusion.cu:66-92, Fusion.h:79-95).
+ */
+int smesh_fuse_get(int kind, const float* acc, int64_t P, int C, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SMESH_H */

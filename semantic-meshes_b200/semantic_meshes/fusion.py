@@ -1,0 +1,217 @@
+"""semantic_meshes.fusion - per-primitive label fusion (python/semantic_meshes/src/Fusion.cu:140-151).
+
+    aggregator = semantic_meshes.fusion.MeshAggregator(primitives=P, classes=C[, aggregator="sum"[, images_equal_weight=0.5]])
+    aggregator.add(primitive_indices, probs[, weights])     # (W,H) ints, (W,H,C) float32, (W,H) float32
+    annotations = aggregator.get()                          # (P, C) float32 numpy
+
+Semantics of include/semantic_meshes/fusion/Mesh.h:57-133 with the aggregator chains of Fusion.cu:46-92 ("sum",
+"summax", "mul"). The accumulator lives on the GPU as a torch tensor; `add` is asynchronous on the current CUDA stream.
+Views may be sharded over several processes / GPUs: every rank adds its views, then `allreduce()` sums the
+accumulators (one NCCL all-reduce) before `get()`.
+"""
+import numpy as np
+
+from . import _lib
+
+_NONE_MATCHED = "None matched from [torch.Tensor, numpy.ndarray, DLPack capsule / __dlpack__]: "
+
+
+def _torch_id_dtypes(torch):
+    return {torch.uint32: _lib.ID_U32, torch.int32: _lib.ID_I32, torch.uint64: _lib.ID_U64, torch.int64: _lib.ID_I64}
+
+
+class MeshAggregator:
+    """One accumulator row of `classes` floats per primitive.
+
+    aggregator: "sum" (default) | "summax" | "mul" - first letter case-insensitive like the reference (Fusion.cu:126).
+    The reference only knows the class counts it was compiled for (CLASSES_NUMS, Fusion.cu:122-125); here `classes` is a
+    run-time value.
+    """
+
+    def __init__(self, primitives, classes, aggregator="sum", images_equal_weight=0.5, device=None):
+        torch = _lib.require_cuda()
+        self._torch = torch
+        primitives, classes = int(primitives), int(classes)
+        if primitives < 0:
+            raise ValueError("MeshAggregator: primitives must be >= 0")
+        if classes < 1:
+            raise ValueError(f"The project does not support the following number of classes: {classes}")
+        name = str(aggregator)
+        name = name[:1].lower() + name[1:]
+        if name not in _lib.KIND:
+            # the reference calls an empty std::function here -> std::bad_function_call -> RuntimeError
+            raise RuntimeError(f"MeshAggregator: unknown aggregator '{aggregator}' (sum, summax, mul)")
+        self.primitives, self.classes = primitives, classes
+        self.aggregator = name
+        self.images_equal_weight = float(images_equal_weight)
+        self._kind = _lib.KIND[name]
+        self._cpad = int(_lib.lib.smesh_fuse_padded_classes(classes))
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._id_dtypes = _torch_id_dtypes(torch)
+        # raw accumulator [P, Cpad] (mul: -log p), per-view pixel counters [P], flat id scratch (grown on demand)
+        self._acc = torch.zeros((primitives, self._cpad), dtype=torch.float32, device=self.device)
+        self._counts = torch.zeros((max(primitives, 1),), dtype=torch.int32, device=self.device)
+        self._ids32 = torch.empty((0,), dtype=torch.int32, device=self.device)
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def _as_tensor(self, obj, what):
+        torch = self._torch
+        if isinstance(obj, torch.Tensor):
+            t = obj
+        elif isinstance(obj, np.ndarray):
+            if any(s < 0 for s in obj.strides) or not obj.flags.writeable:
+                obj = np.ascontiguousarray(obj) if any(s < 0 for s in obj.strides) else obj
+                if not obj.flags.writeable:
+                    obj = obj.copy()
+            t = torch.from_numpy(obj)
+        elif hasattr(obj, "__dlpack__") or type(obj).__name__ == "PyCapsule":
+            t = torch.utils.dlpack.from_dlpack(obj)
+        else:
+            raise ValueError(_NONE_MATCHED + f"{what} has type {type(obj).__name__}")
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        return t
+
+    def _stage(self, primitive_indices, probs, weights):
+        """Validate like Fusion.h:42-64 / Mesh.h:68-74 and move to the device. -> (ids, id_dtype, probs, weights)"""
+        ids = self._as_tensor(primitive_indices, "primitive_indices")
+        pr = self._as_tensor(probs, "probs")
+        id_dtype = self._id_dtypes.get(ids.dtype)
+        if id_dtype is None or ids.dim() != 2:
+            raise ValueError(_NONE_MATCHED + f"primitive_indices must be a rank-2 uint32/int32/uint64/int64 array, got "
+                             f"rank {ids.dim()} {ids.dtype}")
+        if pr.dtype != self._torch.float32 or pr.dim() != 3:
+            raise ValueError(_NONE_MATCHED + f"probs must be a rank-3 float32 array, got rank {pr.dim()} {pr.dtype}")
+        wt = None
+        if weights is not None:
+            wt = self._as_tensor(weights, "weights")
+            if wt.dtype != self._torch.float32 or wt.dim() != 2:
+                raise ValueError(_NONE_MATCHED + f"weights must be a rank-2 float32 array, got rank {wt.dim()} {wt.dtype}")
+        W, H = ids.shape
+        if tuple(pr.shape[:2]) != (W, H) or (wt is not None and tuple(wt.shape) != (W, H)):
+            raise ValueError(f"Primitive image {tuple(ids.shape)}, probs image {tuple(pr.shape[:2])} and weights image "
+                             f"{tuple(wt.shape) if wt is not None else (W, H)} must have the same width and height")
+        if pr.shape[2] != self.classes:
+            raise ValueError(f"probs image has {pr.shape[2]} classes, aggregator was built for {self.classes}")
+        return ids, id_dtype, pr, wt
+
+    def _layout(self, ids, pr, wt):
+        """Pick the pixel order in which the probability image is contiguous, so it is never copied (callers pass
+        `transpose(pred, (1, 0, 2))` views of (H, W, C) network outputs, python/scripts/colorize_mesh.py:66)."""
+        W, H = ids.shape
+        C = self.classes
+        sx, sy, sc = pr.stride()
+        if W * H == 0:
+            return None
+        if (sc == 1 or C == 1) and (sy == C or H == 1) and (sx == H * C or W == 1):
+            x_major = True
+        elif (sc == 1 or C == 1) and (sx == C or W == 1) and (sy == W * C or H == 1):
+            x_major = False
+        else:
+            pr = pr.contiguous()
+            x_major = True
+        if pr.data_ptr() % 16 != 0:
+            pr = pr.clone(memory_format=self._torch.contiguous_format)
+            x_major = True
+        ix, iy = ids.stride()
+        if x_major:
+            n_outer, n_inner, ids_so, ids_si = W, H, ix, iy
+        else:
+            n_outer, n_inner, ids_so, ids_si = H, W, iy, ix
+        w_so = w_si = 0
+        if wt is not None:
+            wx, wy = wt.stride()
+            w_so, w_si = (wx, wy) if x_major else (wy, wx)
+            if not ((w_si == 1 or n_inner == 1) and (w_so == n_inner or n_outer == 1)):
+                wt = wt.contiguous() if x_major else wt.t().contiguous().t()
+                w_so, w_si = n_inner, 1
+        return pr, wt, n_outer, n_inner, ids_so, ids_si, w_so, w_si
+
+    def _scratch(self, npix):
+        if self._ids32.numel() < npix:
+            self._ids32 = self._torch.empty((npix,), dtype=self._torch.int32, device=self.device)
+        return self._ids32
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def add(self, primitive_indices, probs, weights=None):
+        """Fuse one view (ModelAggregator::add, Mesh.h:65-107)."""
+        torch = self._torch
+        ids, id_dtype, pr, wt = self._stage(primitive_indices, probs, weights)
+        lay = self._layout(ids, pr, wt)
+        if lay is None or self.primitives == 0:
+            return
+        pr, wt, n_outer, n_inner, ids_so, ids_si, w_so, w_si = lay
+        with torch.cuda.device(self.device):
+            rc = _lib.lib.smesh_fuse_add(self._kind, ids.data_ptr(), id_dtype, ids_so, ids_si, pr.data_ptr(),
+                                         wt.data_ptr() if wt is not None else None, w_so, w_si, n_outer, n_inner,
+                                         self.classes, self.primitives, self.images_equal_weight,
+                                         self._counts.data_ptr(), self._scratch(n_outer * n_inner).data_ptr(),
+                                         self._acc.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc)
+
+    def add_batch(self, primitive_indices, probs, weights=None):
+        """Extension: fuse B views held in batched device tensors (B,W,H) / (B,W,H,C) / (B,W,H) with one call; the same
+        result as B `add` calls in order, without B trips through Python."""
+        torch = self._torch
+        ids = self._as_tensor(primitive_indices, "primitive_indices")
+        pr = self._as_tensor(probs, "probs")
+        wt = self._as_tensor(weights, "weights") if weights is not None else None
+        if ids.dim() != 3 or pr.dim() != 4 or ids.shape[0] != pr.shape[0]:
+            raise ValueError("add_batch expects (B,W,H) indices and (B,W,H,C) probs")
+        B = ids.shape[0]
+        if B == 0:
+            return
+        ids0, id_dtype, pr0, wt0 = self._stage(ids[0], pr[0], wt[0] if wt is not None else None)
+        lay = self._layout(ids0, pr0, wt0)
+        if lay is None or self.primitives == 0:
+            return
+        pr0c, wt0c, n_outer, n_inner, ids_so, ids_si, w_so, w_si = lay
+        if pr0c.data_ptr() != pr[0].data_ptr() or (wt is not None and wt0c.data_ptr() != wt[0].data_ptr()) \
+                or (pr.stride(0) * 4) % 16 != 0:
+            for b in range(B):  # layouts that need a copy: go view by view
+                self.add(ids[b], pr[b], wt[b] if wt is not None else None)
+            return
+        with torch.cuda.device(self.device):
+            rc = _lib.lib.smesh_fuse_add_batch(self._kind, B, ids.data_ptr(), id_dtype, ids.stride(0), ids_so, ids_si,
+                                               pr.data_ptr(), pr.stride(0), wt.data_ptr() if wt is not None else None,
+                                               wt.stride(0) if wt is not None else 0, w_so, w_si, n_outer, n_inner,
+                                               self.classes, self.primitives, self.images_equal_weight,
+                                               self._counts.data_ptr(), self._scratch(n_outer * n_inner).data_ptr(),
+                                               self._acc.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc)
+
+    def reset(self):
+        """ModelAggregator::reset (Mesh.h:119-122): every row back to the aggregator's zero (mul: -log 1 = 0)."""
+        self._acc.zero_()
+
+    def get(self, device=False):
+        """Per-primitive class distribution (P, C) (Fusion.h:72-76): the accumulator row (mul: exp(-(l - min l))),
+        L1-normalised, NaN/Inf -> 0. numpy by default like the reference; device=True returns the torch CUDA tensor."""
+        torch = self._torch
+        out = torch.empty((self.primitives, self.classes), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib.smesh_fuse_get(self._kind, self._acc.data_ptr(), self.primitives, self.classes, out.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc)
+        return out if device else out.cpu().numpy()
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # extensions for view-sharded multi-GPU runs and checkpointing
+    def allreduce(self, group=None):
+        """Sum the raw accumulators of all ranks in place (one NCCL all-reduce of P x Cpad floats). Every aggregator
+        kind accumulates by addition (mul adds -log p, +inf stays absorbing), so the sum of per-rank accumulators equals
+        the accumulator of all views added on one GPU up to float reassociation."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self._acc, op=dist.ReduceOp.SUM, group=group)
+
+    def state(self):
+        """Raw accumulator (P, C) as a torch CUDA tensor (a view without the alignment padding)."""
+        return self._acc[:, :self.classes]
+
+    def load_state(self, acc):
+        acc = self._as_tensor(acc, "state")
+        if tuple(acc.shape) != (self.primitives, self.classes) or acc.dtype != self._torch.float32:
+            raise ValueError("load_state expects a (primitives, classes) float32 array")
+        self._acc.zero_()
+        self._acc[:, :self.classes] = acc

@@ -1,0 +1,86 @@
+"""semantic_meshes.render - triangle rasterizer (python/semantic_meshes/src/Render.cu:3-24).
+
+    renderer = semantic_meshes.render.triangles(mesh)
+    primitive_indices, depth = renderer.render(camera)
+
+Follows Renderer<T>::render (python/semantic_meshes/include/Renderer.h:25-43): both images are (W, H) device arrays,
+pixel (x, y) at [x, y]; nothing hit = index 0xFFFFFFFF and depth +inf.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .data import Camera, Ply
+
+
+class TriangleRenderer:
+    """Device-resident mesh + scratch; one `render(camera)` per view (include/semantic_meshes/render/TriangleRenderer.h)."""
+
+    def __init__(self, ply, device=None):
+        torch = _lib.require_cuda()
+        if not isinstance(ply, Ply):
+            raise TypeError("render.triangles expects a semantic_meshes.data.Ply")
+        self._torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        verts = np.ascontiguousarray(ply.vertices, dtype=np.float32)
+        faces = np.ascontiguousarray(ply.faces, dtype=np.int32)
+        if faces.size and (faces.min() < 0 or faces.max() >= verts.shape[0]):
+            raise ValueError("render.triangles: face index out of range")
+        self._V, self._F = int(verts.shape[0]), int(faces.shape[0])
+        # what TriangleRenderer's ctor uploads (TriangleRenderer.h:30-39)
+        self._verts = torch.from_numpy(verts).to(self.device)
+        self._faces = torch.from_numpy(faces).to(self.device)
+        self._workspace = None
+        self._workspace_res = None
+
+    def getPrimitivesNum(self):
+        return self._F
+
+    def _ensure_workspace(self, W, H):
+        if self._workspace_res != (W, H):
+            nbytes = ctypes.c_size_t(0)
+            _lib.check(_lib.lib.smesh_raster_workspace_bytes(self._V, self._F, W, H, ctypes.byref(nbytes)))
+            self._workspace = self._torch.empty(nbytes.value, dtype=self._torch.uint8, device=self.device)
+            self._workspace_res = (W, H)
+        return self._workspace
+
+    def render(self, camera, capsule=False):
+        """-> (primitive_indices, depth): torch tensors on the GPU, shapes (W, H).
+
+        primitive_indices is int32 holding the reference's uint32 bit pattern (background 0xFFFFFFFF reads as -1; torch
+        has few uint32 ops) - `MeshAggregator.add` takes it as is. With capsule=True both are returned as DLPack
+        capsules named "dltensor", exactly what the reference returns (Renderer.h:37-41), for
+        `tf.experimental.dlpack.from_dlpack` style consumers.
+        """
+        if not isinstance(camera, Camera):
+            raise TypeError("render expects a semantic_meshes.data.Camera")
+        torch = self._torch
+        W, H = camera.resolution
+        if W < 1 or H < 1:
+            raise ValueError("render: empty resolution")
+        with torch.cuda.device(self.device):
+            ws = self._ensure_workspace(W, H)
+            idx = torch.empty((W, H), dtype=torch.int32, device=self.device)
+            depth = torch.empty((W, H), dtype=torch.float32, device=self.device)
+            R, t = camera.rotation, camera.translation
+            f, c = camera.focal_lengths, camera.principal_point
+            rc = _lib.lib.smesh_raster_render(self._verts.data_ptr(), self._V, self._faces.data_ptr(), self._F,
+                                              R.ctypes.data, t.ctypes.data, f.ctypes.data, c.ctypes.data, W, H,
+                                              ws.data_ptr(), ws.numel(), idx.data_ptr(), depth.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc)
+        if capsule:
+            from torch.utils.dlpack import to_dlpack
+            return to_dlpack(idx.view(torch.uint32)), to_dlpack(depth)
+        return idx, depth
+
+
+def triangles(ply, device=None):
+    """render.triangles(ply) (Render.cu:24, python/semantic_meshes/include/Ply.h:121-124)."""
+    return TriangleRenderer(ply, device=device)
+
+
+def texels(*args, **kwargs):
+    raise NotImplementedError("render.texels (TexturedTriangleRenderer) is outside the B200 hot-path scope; "
+                              "use render.triangles")

@@ -1,0 +1,59 @@
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_DIR = os.path.join(ROOT, "semantic-meshes_b200")
+for p in (ROOT, PKG_DIR):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the oracle (test infrastructure) and the product library are compiled artefacts: build them if a fresh checkout
+    import __graft_entry__
+    __graft_entry__.build(quiet=True)
+
+
+def has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if has_cuda():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+def write_plain_ply(path, verts, faces):
+    """Binary PLY with only what the reference loader accepts: float xyz + `list uchar int vertex_indices`."""
+    verts = np.ascontiguousarray(verts, dtype="<f4")
+    faces = np.ascontiguousarray(faces, dtype="<i4")
+    header = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\n"
+              "property float z\nelement face %d\nproperty list uchar int vertex_indices\nend_header\n"
+              % (verts.shape[0], faces.shape[0]))
+    rec = np.empty(faces.shape[0], dtype=np.dtype([("n", "u1"), ("v", "<i4", (3,))]))
+    rec["n"] = 3
+    rec["v"] = faces
+    with open(path, "wb") as fh:
+        fh.write(header.encode("ascii"))
+        fh.write(verts.tobytes())
+        fh.write(rec.tobytes())

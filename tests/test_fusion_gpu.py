@@ -1,0 +1,279 @@
+"""GPU: MeshAggregator (CUDA, through the C ABI) against the CPU oracle on identical inputs.
+Tolerances: ids / gates / counts are exact; the float accumulator is compared at 1e-5 relative (north_star) because the
+order of float additions differs (atomics) exactly as it does between two runs of the reference itself; `mul` is
+compared at 1e-5 in its log-domain accumulator and at 5e-4 after exp()/normalise (the reference's own run-to-run
+spread there is 1e-4, see tests/test_oracle_fusion.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ["sum", "summax", "mul"]
+
+
+@pytest.fixture(scope="module")
+def sm():
+    import torch
+    import semantic_meshes
+    assert torch.cuda.is_available()
+    return semantic_meshes
+
+
+def make_view(rng, W, H, C, P, block=2, bg=0.1, oob=0.02, dont_care=0.05, zeros=0.02):
+    bx, by = (W + block - 1) // block, (H + block - 1) // block
+    base = rng.integers(0, max(P, 1), size=(bx, by), dtype=np.int64)
+    ids = np.repeat(np.repeat(base, block, 0), block, 1)[:W, :H].astype(np.uint32)
+    ids[rng.random((W, H)) < bg] = 0xFFFFFFFF
+    ids[rng.random((W, H)) < oob] = P + 3
+    logits = rng.normal(size=(W, H, C)).astype(np.float32) * 3
+    e = np.exp(logits - logits.max(-1, keepdims=True))
+    probs = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+    probs[rng.random((W, H)) < dont_care] = 0
+    probs[rng.random((W, H, C)) < zeros] = 0
+    return ids, probs
+
+
+def assert_acc_close(kind, got_acc, exp_acc, rtol=1e-5):
+    if kind == "mul":
+        assert np.array_equal(np.isinf(got_acc), np.isinf(exp_acc))
+        fin = ~np.isinf(exp_acc)
+        np.testing.assert_allclose(got_acc[fin], exp_acc[fin], rtol=rtol, atol=1e-6)
+    else:
+        scale = max(float(np.abs(exp_acc).max()), 1e-30)
+        np.testing.assert_allclose(got_acc, exp_acc, rtol=rtol, atol=1e-6 * scale)
+
+
+def assert_get_close(kind, got, exp):
+    np.testing.assert_allclose(got, exp, rtol=5e-4 if kind == "mul" else 1e-5, atol=5e-6 if kind == "mul" else 1e-7)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("C", [1, 3, 19, 40, 150])
+@pytest.mark.parametrize("iew", [0.5, 0.0])
+def test_parity_with_oracle(sm, kind, C, iew):
+    import torch
+    rng = np.random.default_rng(C * 100 + len(kind))
+    W, H, P = 61, 47, 300  # ragged: 2867 pixels, not a multiple of the tile
+    agg = sm.fusion.MeshAggregator(primitives=P, classes=C, aggregator=kind, images_equal_weight=iew)
+    ref = oracle.Aggregator(P, C, kind, iew)
+    for v in range(3):
+        ids, probs = make_view(rng, W, H, C, P, block=1 + v)
+        wts = (rng.random((W, H)) * 2).astype(np.float32) if v == 1 else None
+        agg.add(torch.from_numpy(ids.view(np.int32)).cuda(), torch.from_numpy(probs).cuda(),
+                None if wts is None else torch.from_numpy(wts).cuda())
+        ref.add(ids, probs, wts)
+    assert_acc_close(kind, agg.state().cpu().numpy(), ref.acc)
+    assert_get_close(kind, agg.get(), ref.get())
+    # counters are handed back clean for the next view
+    assert not agg._counts.any().item()
+    agg.reset()
+    assert not agg.state().any().item()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("iew", [0.5, 0.0, 1.0])
+def test_known_answer_vectors(sm, kind, iew):
+    from test_oracle_fusion import kat_inputs
+    kat = json.load(open(os.path.join(GOLDEN, "fusion_kat.json")))
+    ids, probs = kat_inputs(kat)
+    agg = sm.fusion.MeshAggregator(kat["P"], kat["C"], kind, iew)
+    agg.add(ids, probs)
+    agg.add(ids, probs)
+    exp = np.array(kat["expected"][f"{kind}_{iew}"], dtype=np.float32).reshape(kat["P"], kat["C"])
+    np.testing.assert_allclose(agg.get(), exp, rtol=1e-5, atol=1e-9)
+
+
+def test_golden_from_genuine_reference(sm):
+    data = np.load(os.path.join(GOLDEN, "fusion_ref.npz"))
+    for case in [str(c) for c in data["cases"]]:
+        kind, C, iew = case.split("_")
+        C, iew = int(C[1:]), float(iew[3:])
+        exp = data[f"{case}_get"]
+        agg = sm.fusion.MeshAggregator(exp.shape[0], C, kind, iew)
+        for v in range(3):
+            w = data[f"{case}_weights{v}"] if f"{case}_weights{v}" in data else None
+            agg.add(data[f"{case}_ids{v}"], data[f"{case}_probs{v}"], w)
+        assert_get_close(kind, agg.get(), exp)
+
+
+@pytest.mark.parametrize("dtype", ["uint32", "int32", "uint64", "int64"])
+def test_id_dtypes_and_background(sm, dtype):
+    import torch
+    rng = np.random.default_rng(11)
+    W, H, C, P = 40, 33, 19, 200
+    ids, probs = make_view(rng, W, H, C, P)
+    ref = oracle.Aggregator(P, C)
+    ref.add(ids, probs)
+    wide = ids.astype(np.int64)
+    wide[ids == 0xFFFFFFFF] = -1
+    if dtype.endswith("64"):
+        wide[0, 0] = 2 ** 40 + 5  # must not alias a valid id after truncation
+    if dtype.startswith("u"):
+        arr = np.where(wide < 0, np.iinfo(dtype).max, wide).astype(dtype)
+    else:
+        arr = wide.astype(dtype)
+    if dtype.endswith("64"):
+        ids_ref = ids.copy()
+        ids_ref[0, 0] = 0xFFFFFFFF
+        ref = oracle.Aggregator(P, C)
+        ref.add(ids_ref, probs)
+    for src in (arr, torch.from_numpy(arr.view(dtype.replace("u", ""))).view(getattr(torch, dtype)).cuda()):
+        agg = sm.fusion.MeshAggregator(P, C)
+        agg.add(src, probs)
+        assert_acc_close("sum", agg.state().cpu().numpy(), ref.acc)
+
+
+def test_strided_inputs_are_not_copied(sm):
+    """Callers pass transpose(pred, (1, 0, 2)) views of (H, W, C) network outputs (colorize_mesh.py:66) and (H, W)
+    index images: same result as the contiguous layout."""
+    import torch
+    rng = np.random.default_rng(3)
+    W, H, C, P = 50, 36, 19, 150
+    ids, probs = make_view(rng, W, H, C, P)
+    wts = rng.random((W, H)).astype(np.float32)
+    ref = oracle.Aggregator(P, C)
+    ref.add(ids, probs, wts)
+    pr_hw = torch.from_numpy(np.ascontiguousarray(probs.transpose(1, 0, 2))).cuda()     # (H, W, C)
+    ids_hw = torch.from_numpy(np.ascontiguousarray(ids.view(np.int32).T)).cuda()        # (H, W)
+    w_hw = torch.from_numpy(np.ascontiguousarray(wts.T)).cuda()
+    for ids_t, w_t in ((ids_hw.t(), w_hw.t()), (ids_hw.t().contiguous(), w_hw.t().contiguous())):
+        agg = sm.fusion.MeshAggregator(P, C)
+        agg.add(ids_t, pr_hw.permute(1, 0, 2), w_t)
+        assert_acc_close("sum", agg.state().cpu().numpy(), ref.acc)
+    # class-strided probabilities (C, W, H) -> falls back to one contiguous copy, same numbers
+    agg = sm.fusion.MeshAggregator(P, C)
+    agg.add(ids, torch.from_numpy(np.ascontiguousarray(probs.transpose(2, 0, 1))).cuda().permute(1, 2, 0), wts)
+    assert_acc_close("sum", agg.state().cpu().numpy(), ref.acc)
+    # numpy transposed view on the host
+    agg = sm.fusion.MeshAggregator(P, C)
+    agg.add(np.ascontiguousarray(ids.T).T, np.ascontiguousarray(probs.transpose(1, 0, 2)).transpose(1, 0, 2), wts)
+    assert_acc_close("sum", agg.state().cpu().numpy(), ref.acc)
+
+
+def test_dlpack_capsule_input(sm):
+    import torch
+    from torch.utils.dlpack import to_dlpack
+    rng = np.random.default_rng(4)
+    W, H, C, P = 20, 30, 3, 50
+    ids, probs = make_view(rng, W, H, C, P)
+    ref = oracle.Aggregator(P, C)
+    ref.add(ids, probs)
+    agg = sm.fusion.MeshAggregator(P, C)
+    agg.add(to_dlpack(torch.from_numpy(ids.view(np.int32)).cuda()), to_dlpack(torch.from_numpy(probs).cuda()))
+    assert_acc_close("sum", agg.state().cpu().numpy(), ref.acc)
+
+
+def test_edge_cases(sm):
+    import torch
+    C, P = 19, 10
+    agg = sm.fusion.MeshAggregator(P, C)
+    agg.add(np.zeros((0, 5), dtype=np.uint32), np.zeros((0, 5, C), dtype=np.float32))          # empty view
+    agg.add(np.full((7, 5), 0xFFFFFFFF, dtype=np.uint32), np.full((7, 5, C), 1 / C, dtype=np.float32))  # all background
+    agg.add(np.zeros((7, 5), dtype=np.uint32), np.zeros((7, 5, C), dtype=np.float32))          # all don't-care
+    assert not agg.state().any().item()
+    assert not agg.get().any()
+    # a single face collecting every pixel of a view: n = W*H, weight = iew/n + (1-iew)
+    W, H = 33, 9
+    probs = np.full((W, H, C), 1 / C, dtype=np.float32)
+    agg.add(np.full((W, H), 4, dtype=np.uint32), probs)
+    ref = oracle.Aggregator(P, C)
+    ref.add(np.full((W, H), 4, dtype=np.uint32), probs)
+    assert_acc_close("sum", agg.state().cpu().numpy(), ref.acc)
+    # no primitives at all
+    empty = sm.fusion.MeshAggregator(0, C)
+    empty.add(np.zeros((4, 4), dtype=np.uint32), np.zeros((4, 4, C), dtype=np.float32))
+    assert empty.get().shape == (0, C)
+    # very wide class vector -> direct kernel
+    Cw = 1000
+    rng = np.random.default_rng(9)
+    ids, probs = make_view(rng, 12, 10, Cw, P)
+    wide, ref = sm.fusion.MeshAggregator(P, Cw), oracle.Aggregator(P, Cw)
+    wide.add(ids, probs)
+    ref.add(ids, probs)
+    assert_acc_close("sum", wide.state().cpu().numpy(), ref.acc)
+
+
+def test_error_behaviour(sm):
+    """Same exception types as the reference binding."""
+    C, P = 3, 10
+    agg = sm.fusion.MeshAggregator(P, C)
+    ids = np.zeros((4, 5), dtype=np.uint32)
+    with pytest.raises(ValueError, match="must have the same width and height"):
+        agg.add(ids, np.zeros((5, 4, C), dtype=np.float32))
+    with pytest.raises(ValueError, match="must have the same width and height"):
+        agg.add(ids, np.zeros((4, 5, C), dtype=np.float32), np.zeros((4, 4), dtype=np.float32))
+    with pytest.raises(ValueError, match="None matched"):
+        agg.add(ids.astype(np.float32), np.zeros((4, 5, C), dtype=np.float32))
+    with pytest.raises(ValueError, match="None matched"):
+        agg.add(ids, np.zeros((4, 5, C), dtype=np.float64))
+    with pytest.raises(ValueError, match="None matched"):
+        agg.add(ids.reshape(-1), np.zeros((4, 5, C), dtype=np.float32))
+    with pytest.raises(ValueError, match="None matched"):
+        agg.add([[0]], np.zeros((1, 1, C), dtype=np.float32))
+    with pytest.raises(RuntimeError):
+        sm.fusion.MeshAggregator(P, C, aggregator="median")
+    sm.fusion.MeshAggregator(P, C, aggregator="Sum")  # first letter is case-insensitive (Fusion.cu:126)
+    sm.fusion.MeshAggregator(primitives=P, classes=C, aggregator="mul", images_equal_weight=0.25)
+
+
+def test_add_batch_equals_sequential(sm):
+    import torch
+    rng = np.random.default_rng(21)
+    B, W, H, C, P = 4, 32, 24, 19, 90
+    views = [make_view(rng, W, H, C, P) for _ in range(B)]
+    ids = torch.from_numpy(np.stack([v[0] for v in views]).view(np.int32)).cuda()
+    probs = torch.from_numpy(np.stack([v[1] for v in views])).cuda()
+    a, b = sm.fusion.MeshAggregator(P, C), sm.fusion.MeshAggregator(P, C)
+    a.add_batch(ids, probs)
+    for i in range(B):
+        b.add(ids[i], probs[i])
+    ref = oracle.Aggregator(P, C)
+    for i, p in views:
+        ref.add(i, p)
+    assert_acc_close("sum", a.state().cpu().numpy(), ref.acc)
+    assert_acc_close("sum", b.state().cpu().numpy(), ref.acc)
+
+
+def test_full_size_properties(sm):
+    """Config 3 shape (2 M primitives, 2048x1024x19): too big for the oracle in seconds, so check size-independent
+    properties against a plain torch fp32 statement of the same op (bincount + index_add_), plus linearity."""
+    import torch
+    W, H, C, P = 2048, 1024, 19, 2_000_000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    # 4x4-pixel blocks of random faces, 10 % background
+    base = torch.randint(0, P, (W // 4, H // 4), generator=g, device="cuda", dtype=torch.int32)
+    ids = base.repeat_interleave(4, 0).repeat_interleave(4, 1).contiguous()
+    ids[torch.rand((W, H), generator=g, device="cuda") < 0.1] = -1
+    probs = torch.softmax(torch.randn((W, H, C), generator=g, device="cuda") * 3, -1)
+    probs[torch.rand((W, H), generator=g, device="cuda") < 0.02] = 0
+    agg = sm.fusion.MeshAggregator(P, C)
+    agg.add(ids, probs)
+    acc1 = agg.state().clone()
+
+    flat = ids.reshape(-1).long()
+    valid = flat >= 0
+    n = torch.bincount(flat[valid], minlength=P).float()
+    s = probs.reshape(-1, C).sum(-1)
+    ok = valid & (s > 0.5)
+    w = 0.5 * (1.0 / n[flat.clamp(min=0)]) + 0.5
+    exp = torch.zeros((P, C), device="cuda")
+    exp.index_add_(0, flat[ok], probs.reshape(-1, C)[ok] * w[ok, None])
+    torch.testing.assert_close(acc1, exp, rtol=1e-5, atol=1e-6)
+    # conservation: total mass = sum of accepted pixel weights (each class vector sums to ~1)
+    assert abs(acc1.double().sum().item() - (w[ok].double() * s[ok].double()).sum().item()) < 1e-3 * ok.sum().item() ** 0.5
+    # linearity: the same view again doubles every row
+    agg.add(ids, probs)
+    torch.testing.assert_close(agg.state(), 2 * acc1, rtol=1e-6, atol=1e-7)
+    # get(): rows sum to 1 where touched, 0 elsewhere
+    out = agg.get(device=True)
+    rows = out.sum(-1)
+    touched = torch.zeros(P, dtype=torch.bool, device="cuda")
+    touched[flat[ok]] = True
+    assert torch.allclose(rows[touched], torch.ones_like(rows[touched]), atol=1e-5)
+    assert not out[~touched].any().item()
