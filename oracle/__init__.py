@@ -143,6 +143,23 @@ def fuse_stats(ids, probs, P):
     return a.value, t.value
 
 
+def write_plain_ply(path, verts, faces):
+    """Binary PLY with only what the reference loader accepts (src/data/Ply.cpp:9-15): float xyz vertices and one
+    `list uchar int vertex_indices` face property. Used to hand synthetic meshes to the genuine reference renderer."""
+    verts = np.ascontiguousarray(verts, dtype="<f4")
+    faces = np.ascontiguousarray(faces, dtype="<i4")
+    header = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\n"
+              "property float z\nelement face %d\nproperty list uchar int vertex_indices\nend_header\n"
+              % (verts.shape[0], faces.shape[0]))
+    rec = np.empty(faces.shape[0], dtype=np.dtype([("n", "u1"), ("v", "<i4", (3,))]))
+    rec["n"] = 3
+    rec["v"] = faces
+    with open(path, "wb") as fh:
+        fh.write(header.encode("ascii"))
+        fh.write(verts.tobytes())
+        fh.write(rec.tobytes())
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Genuine reference builds (oracle/_ref). Present in the build container and shipped prebuilt to the GPU box.
 # ---------------------------------------------------------------------------------------------------------------------

@@ -43,17 +43,4 @@ def golden_dir():
     return GOLDEN
 
 
-def write_plain_ply(path, verts, faces):
-    """Binary PLY with only what the reference loader accepts: float xyz + `list uchar int vertex_indices`."""
-    verts = np.ascontiguousarray(verts, dtype="<f4")
-    faces = np.ascontiguousarray(faces, dtype="<i4")
-    header = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\n"
-              "property float z\nelement face %d\nproperty list uchar int vertex_indices\nend_header\n"
-              % (verts.shape[0], faces.shape[0]))
-    rec = np.empty(faces.shape[0], dtype=np.dtype([("n", "u1"), ("v", "<i4", (3,))]))
-    rec["n"] = 3
-    rec["v"] = faces
-    with open(path, "wb") as fh:
-        fh.write(header.encode("ascii"))
-        fh.write(verts.tobytes())
-        fh.write(rec.tobytes())
+from oracle import write_plain_ply  # noqa: E402,F401  (re-exported for the tests)
