@@ -68,20 +68,31 @@ const char* smesh_version(void);
  * (camera-space vertex cache, per-view ray tables, packed 64-bit depth|index buffer, large-triangle queue). */
 int smesh_raster_workspace_bytes(int64_t V, int64_t F, int W, int H, size_t* bytes_host);
 
+/* Optional per-face mesh property (1 byte per face) that lets the rasterizer drop triangles far outside the image
+ * without testing them (results stay identical, see smesh_raster.cu far_offscreen()). */
+#define SMESH_FACE_WELL_SHAPED 1 /* sine of the smallest angle >= 0.1 */
+
+/* flags_out uint8[F] = SMESH_FACE_WELL_SHAPED or 0 per face; view independent, compute once per mesh. */
+int smesh_raster_face_flags(const float* verts, int64_t V, const int32_t* faces, int64_t F, uint8_t* flags_out,
+                            void* stream);
+
 /*
  * Render one view: per pixel the index of the nearest hit triangle and its camera-space depth z.
  *   verts   float32[V][3], faces int32[F][3]      (what TriangleRenderer's ctor uploads, TriangleRenderer.h:30-39)
+ *   face_flags uint8[F] from smesh_raster_face_flags, or NULL (every triangle takes the exact per-pixel path)
  *   R_host  float[9] row-major rotation, t_host float[3]   (Camera::extr, include/semantic_meshes/render/Camera.h:12)
  *   f_host  double[2] focal lengths, c_host double[2] principal point (Camera::intr; the Python Camera rounds its
  *           inputs to float first and then widens, python/semantic_meshes/include/Camera.h:19-54 - the caller does it)
  *   W, H    Camera::resolution (1 <= W, H <= 65536)
+ *   workspace  device scratch of smesh_raster_workspace_bytes(V, F, W, H) bytes; ZERO-FILL it once after allocating it
+ *           (it caches a per-pixel table keyed by the intrinsics) and keep it for the next views of the same mesh
  *   idx_out uint32[W][H] (0xFFFFFFFF where nothing is hit), depth_out float32[W][H] (+inf where nothing is hit)
  * Results are bit-identical to the reference kernel as compiled by nvcc 12.9 for sm_100a, with the one documented
  * strengthening that exact depth ties go to the lowest triangle index (the reference is order-dependent there).
  */
-int smesh_raster_render(const float* verts, int64_t V, const int32_t* faces, int64_t F, const float* R_host,
-                        const float* t_host, const double* f_host, const double* c_host, int W, int H, void* workspace,
-                        size_t workspace_bytes, uint32_t* idx_out, float* depth_out, void* stream);
+int smesh_raster_render(const float* verts, int64_t V, const int32_t* faces, int64_t F, const uint8_t* face_flags,
+                        const float* R_host, const float* t_host, const double* f_host, const double* c_host, int W, int H,
+                        void* workspace, size_t workspace_bytes, uint32_t* idx_out, float* depth_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Label fusion: replaces ModelAggregator::{add1,add2,get,reset} (python/semantic_meshes/include/Fusion.h:42-76) ->
@@ -96,52 +107,60 @@ int smesh_raster_render(const float* verts, int64_t V, const int32_t* faces, int
 int smesh_fuse_padded_classes(int C);
 
 /*
- * One view into the accumulator = ModelAggregator::add (Mesh.h:65-107). Launches: per-face pixel count (Mesh.h:90-93),
- * the gated, weighted scatter (Mesh.h:94-106), and the reset of the touched counters.
+ * Per-view pixel counters. counts is uint32[P] device scratch owned by the caller; every call that counts a view takes
+ * a `count_epoch`:
+ *   1..255  tagged mode (normal): a word holds (epoch << 24) | n. The view first raises the words it touches to its own
+ *           epoch and then counts, so nothing has to be cleared between views; the caller hands out strictly increasing
+ *           epochs and zero-fills counts before starting over at 1 (and before the first use). Needs n_pix < 2^24.
+ *   0       untagged mode: counts must be all-zero on entry and is all-zero again on completion (an extra clear launch);
+ *           for images of 2^24 pixels or more.
+ *
+ * smesh_fuse_add: one view into the accumulator = ModelAggregator::add (Mesh.h:65-107). Launches: per-face pixel count
+ * (Mesh.h:90-93) and the gated, weighted scatter (Mesh.h:94-106).
  *
  * Pixels are addressed by a flat index i = outer*n_inner + inner (n_pix = n_outer*n_inner); the caller picks
  * outer/inner so that the probability image is contiguous in that order:
- *   probs    float32[n_pix][C]  (16-byte aligned; class stride 1)
+ *   probs    float32[n_pix][C]  (class stride 1; 16-byte aligned for the fast path)
  *   ids      element (outer, inner) at ids[outer*ids_stride_outer + inner*ids_stride_inner] (strides in elements),
  *            type id_dtype; a pixel is background unless 0 <= id < P (Mesh.h:95)
- *   weights  NULL (= 1.0f everywhere, Mesh.h:109-117) or float32, element (outer, inner) at
- *            weights[outer*w_stride_outer + inner*w_stride_inner]
- *   counts   uint32[P] scratch, must be all-zero on entry, is all-zero again on completion
- *   ids32    uint32[n_pix] scratch (flat-order copy of the ids, 0xFFFFFFFF for background)
+ *   weights  NULL (= 1.0f everywhere, Mesh.h:109-117) or float32 contiguous in the same flat order
+ *            (w_stride_inner == 1, w_stride_outer == n_inner)
+ *   ids32    uint32[n_pix] scratch (flat-order copy of the ids, 0xFFFFFFFF for background; untouched when the ids are
+ *            already 32-bit and flat)
  *   acc      float32[P][Cpad]
  *   iew      images_equal_weight (Mesh.h:57,102)
  * SMESH_ERR_UNSUPPORTED if C > 4096 or P >= 2^32 - 1.
  */
 int smesh_fuse_add(int kind, const void* ids, int id_dtype, int64_t ids_stride_outer, int64_t ids_stride_inner,
                    const float* probs, const float* weights, int64_t w_stride_outer, int64_t w_stride_inner,
-                   int64_t n_outer, int64_t n_inner, int C, int64_t P, float iew, uint32_t* counts, uint32_t* ids32,
-                   float* acc, void* stream);
+                   int64_t n_outer, int64_t n_inner, int C, int64_t P, float iew, uint32_t* counts, uint32_t count_epoch,
+                   uint32_t* ids32, float* acc, void* stream);
 
 /*
- * The three stages of smesh_fuse_add as separate calls (a caller that adds the same index image with several
- * predictions can count once; bench.py times the scatter stage alone with them). Pixels in flat order:
- *   smesh_fuse_count    per-face pixel count (Mesh.h:90-93) of ids (any id_dtype, strided) into counts[P] (+=, so counts
- *                       must be zero on entry); ids32_out (may be NULL) receives the flat uint32 copy, background
- *                       and out-of-range ids as 0xFFFFFFFF
+ * The stages of smesh_fuse_add as separate calls (a caller that adds the same index image with several predictions can
+ * count once; bench.py times the scatter stage alone with them). Pixels in flat order:
+ *   smesh_fuse_count    per-face pixel count (Mesh.h:90-93) of ids (any id_dtype, strided) into counts[P]; ids32_out
+ *                       (may be NULL) receives the flat uint32 copy, background and out-of-range ids as 0xFFFFFFFF
  *   smesh_fuse_scatter  gate + weight + accumulate (Mesh.h:94-106) from flat uint32 ids (anything >= P is background),
- *                       flat probs [n_pix][C], flat weights (NULL = 1) and the counts of the same view
- *   smesh_fuse_clear    counts[id] = 0 for every id < P in ids32
+ *                       flat probs [n_pix][C], flat weights (NULL = 1) and the counts of the same view / same epoch
+ *   smesh_fuse_clear    counts[id] = 0 for every id < P in ids32 (what count_epoch 0 needs after the scatter)
  */
 int smesh_fuse_count(const void* ids, int id_dtype, int64_t ids_stride_outer, int64_t ids_stride_inner, int64_t n_outer,
-                     int64_t n_inner, int64_t P, uint32_t* counts, uint32_t* ids32_out, void* stream);
+                     int64_t n_inner, int64_t P, uint32_t* counts, uint32_t count_epoch, uint32_t* ids32_out, void* stream);
 int smesh_fuse_scatter(int kind, const uint32_t* ids32, const float* probs, const float* weights, int64_t n_pix, int C,
-                       int64_t P, float iew, const uint32_t* counts, float* acc, void* stream);
+                       int64_t P, float iew, const uint32_t* counts, uint32_t count_epoch, float* acc, void* stream);
 int smesh_fuse_clear(const uint32_t* ids32, int64_t n_pix, int64_t P, uint32_t* counts, void* stream);
 
 /*
  * A batch of B views with identical shapes, view b at ids + b*ids_stride_view (elements), probs + b*probs_stride_view
- * (floats), weights + b*w_stride_view (floats, if weights != NULL). Equivalent to B calls of smesh_fuse_add in order.
+ * (floats), weights + b*w_stride_view (floats, if weights != NULL). Equivalent to B calls of smesh_fuse_add in order with
+ * epochs count_epoch0, count_epoch0 + 1, ... (all <= 255), or all 0.
  */
 int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id_dtype, int64_t ids_stride_view,
                          int64_t ids_stride_outer, int64_t ids_stride_inner, const float* probs,
                          int64_t probs_stride_view, const float* weights, int64_t w_stride_view, int64_t w_stride_outer,
                          int64_t w_stride_inner, int64_t n_outer, int64_t n_inner, int C, int64_t P, float iew,
-                         uint32_t* counts, uint32_t* ids32, float* acc, void* stream);
+                         uint32_t* counts, uint32_t count_epoch0, uint32_t* ids32, float* acc, void* stream);
 
 /*
  * ModelAggregator::get (Fusion.h:72-76): out float32[P][C] = per-face class distribution: the accumulator row

@@ -18,6 +18,7 @@
 #include "smesh_common.cuh"
 
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace smesh {
 namespace fuse {
@@ -117,7 +118,15 @@ __device__ __forceinline__ float neg_log_pow(float p, float w)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // 1. / 3. per-face pixel count of one view and its reset
+//
+// counts[id] is a tagged word: (epoch << 24) | n. A view with epoch e first raises the word to at least e << 24
+// (atomicMax) and then adds its pixels, so words left over from earlier views (smaller epoch) never need clearing; the
+// caller zero-fills the array only when the 8-bit epoch wraps. epoch 0 = untagged 32-bit counts + clear_kernel afterwards
+// (images with >= 2^24 pixels).
 // ---------------------------------------------------------------------------------------------------------------------
+
+constexpr uint32_t COUNT_BITS = 24;
+constexpr uint32_t COUNT_MASK = (1u << COUNT_BITS) - 1u;
 
 // Mesh.h:95 `primitive_index < rows()` on a size_t: negative values wrap to huge numbers and fail the test.
 __device__ __forceinline__ uint32_t sanitize_id(uint32_t raw, int64_t P)
@@ -137,37 +146,59 @@ __device__ __forceinline__ uint32_t sanitize_id(int64_t raw, int64_t P)
   return (raw >= 0 && raw < P) ? (uint32_t) raw : INVALID_ID;
 }
 
+constexpr int COUNT_UNROLL = 4; // independent 32-pixel groups per warp iteration (loads in flight per lane)
+
 template <typename IdT>
 __global__ void __launch_bounds__(256) count_kernel(const IdT* __restrict__ ids, int64_t stride_outer, int64_t stride_inner,
                                                     int64_t n_inner, int64_t npix, int64_t P, uint32_t* __restrict__ counts,
-                                                    uint32_t* __restrict__ ids32, int flat)
+                                                    uint32_t* __restrict__ ids32, int flat, uint32_t epoch)
 {
-  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  uint32_t id = INVALID_ID;
-  if (i < npix)
+  const int64_t warp_global = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+  const uint32_t tag = epoch << COUNT_BITS;
+  for (int64_t base = warp_global * (32 * COUNT_UNROLL); base < npix; base += nwarps * (32 * COUNT_UNROLL))
   {
-    int64_t off = i;
-    if (!flat)
+    uint32_t id[COUNT_UNROLL];
+#pragma unroll
+    for (int k = 0; k < COUNT_UNROLL; k++)
     {
-      const int64_t o = i / n_inner, in = i - o * n_inner;
-      off = o * stride_outer + in * stride_inner;
+      const int64_t i = base + k * 32 + lane;
+      id[k] = INVALID_ID;
+      if (i < npix)
+      {
+        int64_t off = i;
+        if (!flat)
+        {
+          const int64_t o = i / n_inner, in = i - o * n_inner;
+          off = o * stride_outer + in * stride_inner;
+        }
+        id[k] = sanitize_id(ids[off], P);
+      }
     }
-    id = sanitize_id(ids[off], P);
-    if (ids32 != nullptr)
+#pragma unroll
+    for (int k = 0; k < COUNT_UNROLL; k++)
     {
-      ids32[i] = id;
+      const int64_t i = base + k * 32 + lane;
+      if (ids32 != nullptr && i < npix)
+      {
+        ids32[i] = id[k];
+      }
+      // one atomic per run of equal ids inside the 32-pixel group
+      const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, id[k], 1);
+      const bool head = (lane == 0) || (prev != id[k]);
+      const uint32_t headmask = __ballot_sync(0xFFFFFFFFu, head);
+      if (head && id[k] != INVALID_ID)
+      {
+        const uint32_t above = headmask & ~((2u << lane) - 1u);
+        const int next = above ? (__ffs(above) - 1) : 32;
+        if (epoch != 0)
+        {
+          atomicMax(counts + id[k], tag);
+        }
+        atomicAdd(counts + id[k], (uint32_t) (next - lane));
+      }
     }
-  }
-  // one atomic per run of equal ids inside the warp
-  const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, id, 1);
-  const bool head = (lane == 0) || (prev != id);
-  const uint32_t headmask = __ballot_sync(0xFFFFFFFFu, head);
-  if (head && id != INVALID_ID)
-  {
-    const uint32_t above = headmask & ~((2u << lane) - 1u);
-    const int next = above ? (__ffs(above) - 1) : 32;
-    atomicAdd(counts + id, (uint32_t) (next - lane));
   }
 }
 
@@ -178,7 +209,7 @@ __global__ void __launch_bounds__(256) clear_kernel(const uint32_t* __restrict__
   if (i < npix)
   {
     const uint32_t id = ids32[i];
-    if ((int64_t) id < P)
+    if ((int64_t) id < P && (i == 0 || ids32[i - 1] != id))
     {
       counts[id] = 0;
     }
@@ -194,31 +225,68 @@ struct ScatterArgs
   const float* probs;      // [npix][C]
   const uint32_t* ids;     // [npix] flat order; anything >= P is background
   const float* weights;    // NULL or [npix]
-  const uint32_t* counts;  // [P]
+  const uint32_t* counts;  // [P] tagged pixel counts of this view
   float* acc;              // [P][Cpad]
   int64_t npix;
   int64_t P;
   int64_t ntiles;
   int C, Cpad;
   int stages;
+  uint32_t count_mask;     // COUNT_MASK with a tagged epoch, 0xFFFFFFFF without
+  uint32_t run_cap;        // power of two <= 32: runs of equal ids are cut every run_cap lanes
   float iew;
 };
 
-// Shared memory: [stages][NW*32*C] floats | per consumer warp {w[32], aux[32], run_span[32], run_id[32]} | full[stages], empty[stages]
+constexpr int CH = 20; // classes held in registers per pass (multiple of 4); C = 19 is one pass
+
+// One pixel's classes [c0, c0 + CH) from shared memory into registers, zero beyond C. `al` = largest power of two
+// <= 4 dividing C (and c0): rows of a C % 4 == 0 image are 16-byte aligned and read with 128-bit loads (a lane stride of
+// C words would otherwise be an 8-way bank conflict at C = 40), C % 2 == 0 with 64-bit loads; odd C is conflict-free.
+__device__ __forceinline__ void load_chunk(const float* __restrict__ p, int nvalid, int al, float (&v)[CH])
+{
+  if (al == 4 && nvalid == CH)
+  {
+#pragma unroll
+    for (int j = 0; j < CH / 4; j++)
+    {
+      const float4 t = *reinterpret_cast<const float4*>(p + 4 * j);
+      v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+  }
+  else if (al >= 2 && nvalid == CH)
+  {
+#pragma unroll
+    for (int j = 0; j < CH / 2; j++)
+    {
+      const float2 t = *reinterpret_cast<const float2*>(p + 2 * j);
+      v[2 * j + 0] = t.x; v[2 * j + 1] = t.y;
+    }
+  }
+  else
+  {
+#pragma unroll
+    for (int k = 0; k < CH; k++)
+    {
+      v[k] = (k < nvalid) ? p[k] : 0.0f;
+    }
+  }
+}
+
+// Shared memory: [stages][NW*32*C] floats | full[stages], empty[stages] mbarriers
 template <int KIND, int CT>
 __global__ void __launch_bounds__(288) scatter_kernel(ScatterArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int C = CT > 0 ? CT : a.C;
   const int Cpad = CT > 0 ? ((CT + 3) & ~3) : a.Cpad;
+  const int al = (C % 4 == 0) ? 4 : ((C % 2 == 0) ? 2 : 1);
   const int NW = (int) (blockDim.x >> 5) - 1; // consumer warps; warp 0 produces
   const int tile_px = NW * 32;
   const size_t stage_floats = (size_t) tile_px * C;
   const int stages = a.stages;
 
   float* stage_base = reinterpret_cast<float*>(smem_raw);
-  uint32_t* scratch = reinterpret_cast<uint32_t*>(stage_base + stage_floats * stages);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(scratch + (size_t) NW * 128);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + stage_floats * stages);
   uint64_t* empty_bar = full_bar + stages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -240,14 +308,14 @@ __global__ void __launch_bounds__(288) scatter_kernel(ScatterArgs a)
     if (lane == 0)
     {
       const uint64_t policy = l2_evict_first_policy();
-      int it = 0;
-      for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++)
+      int s = 0;
+      uint32_t use_parity = 1; // parity of the PREVIOUS use of stage s; the first pass over the ring does not wait
+      bool first_pass = true;
+      for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
       {
-        const int s = it % stages;
-        const int use = it / stages;
-        if (use > 0)
+        if (!first_pass)
         {
-          mbar_wait(empty_bar + s, (uint32_t) ((use - 1) & 1));
+          mbar_wait(empty_bar + s, use_parity);
         }
         const int64_t px0 = tile * tile_px;
         const int64_t px_n = min((int64_t) tile_px, a.npix - px0);
@@ -265,71 +333,107 @@ __global__ void __launch_bounds__(288) scatter_kernel(ScatterArgs a)
         {
           bulk_g2s(dst, src, bulk_bytes, full_bar + s, policy);
         }
+        if (++s == stages)
+        {
+          s = 0;
+          first_pass = false;
+          use_parity ^= 1u;
+        }
       }
     }
     return;
   }
 
-  // ===== consumers =====
+  // ===== consumers: warp cw owns pixels [cw*32, cw*32+32) of every tile, lane = pixel =====
   const int cw = warp - 1;
-  float* wbuf = reinterpret_cast<float*>(scratch + (size_t) cw * 128);
-  uint32_t* run_span = scratch + (size_t) cw * 128 + 64;
-  uint32_t* run_id = scratch + (size_t) cw * 128 + 96;
-  const int nchunks = Cpad >> 2;
+  const int64_t lane_px = (int64_t) cw * 32 + lane;      // pixel of this lane inside a tile
+  const int64_t tile_stride = gridDim.x;
+  const uint32_t P32 = (uint32_t) a.P;                   // P < 2^32 - 1 (checked on the host)
+  const bool has_weights = a.weights != nullptr;
+  const uint32_t run_cap = a.run_cap;                    // power of two: longest run reduced by one reduction
 
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++)
+  // Software pipeline of the per-pixel side inputs (all L2 gathers): while tile t is processed, the id / weight of tile
+  // t+2 and the pixel count (which needs the id) of tile t+1 are in flight.
+  auto load_id = [&](int64_t t) -> uint32_t {
+    const int64_t i = t * tile_px + lane_px;
+    return (t < a.ntiles && i < a.npix) ? __ldg(a.ids + i) : INVALID_ID;
+  };
+  auto load_wt = [&](int64_t t) -> float {
+    const int64_t i = t * tile_px + lane_px;
+    return (has_weights && t < a.ntiles && i < a.npix) ? __ldg(a.weights + i) : 1.0f;
+  };
+  auto load_n = [&](uint32_t pid) -> uint32_t { return pid < P32 ? __ldg(a.counts + pid) : 1u; };
+
+  int64_t tile = blockIdx.x;
+  uint32_t id = load_id(tile), id1 = load_id(tile + tile_stride);
+  float wt = load_wt(tile), wt1 = load_wt(tile + tile_stride);
+  uint32_t n = load_n(id);
+
+  int s = 0;
+  uint32_t parity = 0;
+  const float* stage_ptr = stage_base + (size_t) lane_px * C;
+  for (; tile < a.ntiles; tile += tile_stride)
   {
-    const int s = it % stages;
-    const uint32_t parity = (uint32_t) ((it / stages) & 1);
-    const int64_t i = tile * tile_px + (int64_t) cw * 32 + lane;
+    const uint32_t id2 = load_id(tile + 2 * tile_stride);
+    const float wt2 = load_wt(tile + 2 * tile_stride);
+    const uint32_t n1 = load_n(id1);
 
-    // independent of the probability tile: issue before waiting on it
-    uint32_t id = INVALID_ID;
-    float wt = 1.0f;
-    uint32_t n = 1;
-    if (i < a.npix)
+    const bool valid = id < P32;
+    mbar_wait(full_bar + s, parity);
+    const float* row = stage_ptr + stage_floats * s;
+
+    // ---- gate (Mesh.h:95-98): sequential float sum of the class vector > 0.5 ----
+    float v[CH];
+    float sum = 0.0f, best = 0.0f;
+    int best_c = 0;
+    if (C <= CH)
     {
-      id = __ldg(a.ids + i);
-      if (a.weights != nullptr)
+      load_chunk(row, C, al, v); // the whole class vector, zero-padded to CH
+      if (KIND == SMESH_KIND_SUMMAX)
       {
-        wt = __ldg(a.weights + i);
+        best = v[0];
+      }
+#pragma unroll
+      for (int k = 0; k < CH; k++)
+      {
+        if (k < C)
+        {
+          sum = __fadd_rn(sum, v[k]);
+          if (KIND == SMESH_KIND_SUMMAX && v[k] > best) // first maximum, strict > (tt/tensor/util/ArgComp.h:3-18)
+          {
+            best = v[k];
+            best_c = k;
+          }
+        }
       }
     }
-    const bool valid = (int64_t) id < a.P;
-    if (valid)
-    {
-      n = __ldg(a.counts + id);
-    }
-
-    mbar_wait(full_bar + s, parity);
-    const float* tile_s = stage_base + stage_floats * s + (size_t) cw * 32 * C;
-    const float* row = tile_s + (size_t) lane * C;
-
-    // ---- phase A: lane = pixel. Gate (Mesh.h:95-98): sequential float sum of the class vector > 0.5 ----
-    float sum = 0.0f;
-    float best = 0.0f;
-    int best_c = 0;
-    if (valid)
+    else
     {
       if (KIND == SMESH_KIND_SUMMAX)
       {
         best = row[0];
       }
-#pragma unroll 8
-      for (int c = 0; c < C; c++)
+      for (int c0 = 0; c0 < C; c0 += CH)
       {
-        const float p = row[c];
-        sum = __fadd_rn(sum, p);
-        if (KIND == SMESH_KIND_SUMMAX && p > best) // first maximum, strict > (tt/tensor/util/ArgComp.h:3-18)
+        const int nv = min(CH, C - c0);
+        load_chunk(row + c0, nv, al, v);
+#pragma unroll
+        for (int k = 0; k < CH; k++)
         {
-          best = p;
-          best_c = c;
+          if (k < nv)
+          {
+            sum = __fadd_rn(sum, v[k]);
+            if (KIND == SMESH_KIND_SUMMAX && v[k] > best)
+            {
+              best = v[k];
+              best_c = c0 + k;
+            }
+          }
         }
       }
     }
     const bool ok = valid && (sum > 0.5f);
-    const float w = pixel_weight(a.iew, n, wt);
+    const float w = pixel_weight(a.iew, n & a.count_mask, wt);
 
     if constexpr (KIND == SMESH_KIND_SUMMAX)
     {
@@ -341,61 +445,78 @@ __global__ void __launch_bounds__(288) scatter_kernel(ScatterArgs a)
     }
     else
     {
-      // ---- runs of equal face id among consecutive accepted pixels of this warp ----
+      // ---- runs of equal face id among consecutive accepted pixels of this warp, cut every run_cap lanes ----
       const uint32_t key = ok ? id : INVALID_ID;
       const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, key, 1);
-      const bool head = ok && (lane == 0 || prev != key);
+      const bool head = ok && (lane == 0 || prev != key || (lane & (run_cap - 1)) == 0);
       const uint32_t headmask = __ballot_sync(0xFFFFFFFFu, head);
       const uint32_t okmask = __ballot_sync(0xFFFFFFFFu, ok);
-      wbuf[lane] = w;
-      if (head)
-      {
-        const int r = __popc(headmask & ((1u << lane) - 1u));
-        const uint32_t brk = (headmask | ~okmask) & ~((2u << lane) - 1u);
-        const uint32_t end = brk ? (uint32_t) (__ffs(brk) - 1) : 32u;
-        run_span[r] = (uint32_t) lane | (end << 8);
-        run_id[r] = id;
-      }
-      __syncwarp();
+      const uint32_t brk = (headmask | ~okmask) & ~((2u << lane) - 1u);
+      const int end = ok ? (brk ? (__ffs(brk) - 1) : 32) : lane + 1; // one past the last pixel of this lane's run
+      const int maxlen = (int) __reduce_max_sync(0xFFFFFFFFu, (unsigned) (head ? end - lane : 0));
+      float* dst = a.acc + (size_t) (ok ? id : 0) * Cpad;
 
-      // ---- phase B: lane = (run, 4-class chunk) ----
-      const int nitems = __popc(headmask) * nchunks;
-      for (int item = lane; item < nitems; item += 32)
+      for (int c0 = 0; c0 < C; c0 += CH)
       {
-        const int r = item / nchunks;
-        const int c0 = (item - r * nchunks) << 2;
-        const uint32_t span = run_span[r];
-        const int p_begin = (int) (span & 0xFF), p_end = (int) (span >> 8);
-        const bool h1 = c0 + 1 < C, h2 = c0 + 2 < C, h3 = c0 + 3 < C;
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-        for (int p = p_begin; p < p_end; p++)
+        const int nv = min(CH, C - c0);
+        if (C > CH)
         {
-          const float pw = wbuf[p];
-          const float* q = tile_s + (size_t) p * C + c0;
+          load_chunk(row + c0, nv, al, v);
+        }
+#pragma unroll
+        for (int k = 0; k < CH; k++)
+        {
           if (KIND == SMESH_KIND_SUM)
           {
-            // weighted::sum (tt/aggregator/MiscOps.h:83-93): acc += probs * w
-            a0 = __fadd_rn(a0, __fmul_rn(q[0], pw));
-            if (h1) a1 = __fadd_rn(a1, __fmul_rn(q[1], pw));
-            if (h2) a2 = __fadd_rn(a2, __fmul_rn(q[2], pw));
-            if (h3) a3 = __fadd_rn(a3, __fmul_rn(q[3], pw));
+            v[k] = __fmul_rn(v[k], w); // weighted::sum (tt/aggregator/MiscOps.h:83-93): acc += probs * w
           }
           else
           {
-            a0 = __fadd_rn(a0, neg_log_pow(q[0], pw));
-            if (h1) a1 = __fadd_rn(a1, neg_log_pow(q[1], pw));
-            if (h2) a2 = __fadd_rn(a2, neg_log_pow(q[2], pw));
-            if (h3) a3 = __fadd_rn(a3, neg_log_pow(q[3], pw));
+            v[k] = (k < nv && ok) ? neg_log_pow(v[k], w) : 0.0f;
           }
         }
-        red_add_v4(a.acc + (size_t) run_id[r] * Cpad + c0, a0, a1, a2, a3);
+        // segmented suffix sum over the run (log2(longest run) shuffle rounds, warp-uniform)
+        for (int d = 1; d < maxlen; d <<= 1)
+        {
+          const bool take = lane + d < end;
+#pragma unroll
+          for (int k = 0; k < CH; k++)
+          {
+            const float t = __shfl_down_sync(0xFFFFFFFFu, v[k], d);
+            if (take)
+            {
+              v[k] = __fadd_rn(v[k], t);
+            }
+          }
+        }
+        // the head of each run owns the run's sum: one 128-bit reduction per 4 classes into the padded row
+        if (head)
+        {
+#pragma unroll
+          for (int j = 0; j < CH / 4; j++)
+          {
+            if (4 * j < nv)
+            {
+              red_add_v4(dst + c0 + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          }
+        }
       }
     }
+
     __syncwarp();
     if (lane == 0)
     {
       mbar_arrive(empty_bar + s);
     }
+    if (++s == stages)
+    {
+      s = 0;
+      parity ^= 1u;
+    }
+    id = id1; id1 = id2;
+    wt = wt1; wt1 = wt2;
+    n = n1;
   }
 }
 
@@ -431,7 +552,7 @@ __global__ void __launch_bounds__(256) scatter_direct_kernel(ScatterArgs a)
   {
     return;
   }
-  const float w = pixel_weight(a.iew, a.counts[id], a.weights ? a.weights[i] : 1.0f);
+  const float w = pixel_weight(a.iew, a.counts[id] & a.count_mask, a.weights ? a.weights[i] : 1.0f);
   float* dst = a.acc + (size_t) id * a.Cpad;
   if (KIND == SMESH_KIND_SUMMAX)
   {
@@ -507,18 +628,32 @@ struct RingConfig
 
 static bool ring_config(int C, RingConfig& cfg)
 {
-  if (C <= 24) { cfg = {8, 4}; return true; }
-  if (C <= 48) { cfg = {4, 4}; return true; }
-  if (C <= 96) { cfg = {4, 3}; return true; }
-  if (C <= 192) { cfg = {4, 2}; return true; }
-  if (C <= 400) { cfg = {2, 2}; return true; }
-  if (C <= 800) { cfg = {1, 2}; return true; }
-  return false;
+  // consumer warps x stages; one stage = consumer_warps * 32 pixels * C floats (19.5 KB at C = 19)
+  if (C <= 24) { cfg = {8, 3}; }
+  else if (C <= 48) { cfg = {4, 4}; }
+  else if (C <= 96) { cfg = {4, 3}; }
+  else if (C <= 192) { cfg = {4, 2}; }
+  else if (C <= 400) { cfg = {2, 2}; }
+  else if (C <= 800) { cfg = {1, 2}; }
+  else { return false; }
+  // tuning overrides (profiling only)
+  static const int env_nw = getenv("SMESH_SCATTER_NW") ? atoi(getenv("SMESH_SCATTER_NW")) : 0;
+  static const int env_stages = getenv("SMESH_SCATTER_STAGES") ? atoi(getenv("SMESH_SCATTER_STAGES")) : 0;
+  if (env_nw >= 1 && env_nw <= 8) cfg.consumer_warps = env_nw;
+  if (env_stages >= 2 && env_stages <= 8) cfg.stages = env_stages;
+  return true;
+}
+
+static uint32_t scatter_run_cap()
+{
+  // longest run of equal face ids folded into one reduction: fewer shuffle rounds (log2) vs more reductions
+  static const int env = getenv("SMESH_SCATTER_RUNCAP") ? atoi(getenv("SMESH_SCATTER_RUNCAP")) : 0;
+  return (env == 1 || env == 2 || env == 4 || env == 8 || env == 16 || env == 32) ? (uint32_t) env : 32u;
 }
 
 static size_t ring_smem_bytes(int C, const RingConfig& cfg)
 {
-  return (size_t) cfg.stages * cfg.consumer_warps * 32 * C * 4 + (size_t) cfg.consumer_warps * 128 * 4 + (size_t) cfg.stages * 16;
+  return (size_t) cfg.stages * cfg.consumer_warps * 32 * C * 4 + (size_t) cfg.stages * 16;
 }
 
 template <int KIND, int CT>
@@ -583,56 +718,53 @@ static int launch_scatter(const ScatterArgs& args, cudaStream_t stream)
 
 template <typename IdT>
 static int launch_count(const void* ids, int64_t so, int64_t si, int64_t n_inner, int64_t npix, int64_t P, uint32_t* counts,
-                        uint32_t* ids32, bool flat, cudaStream_t stream)
+                        uint32_t* ids32, bool flat, uint32_t epoch, cudaStream_t stream)
 {
-  const int64_t blocks = (npix + 255) / 256;
+  const int64_t per_block = (256 / 32) * 32 * COUNT_UNROLL;
+  int64_t blocks = (npix + per_block - 1) / per_block;
+  const int64_t cap = (int64_t) num_sms() * 8;
+  if (blocks > cap) blocks = cap;
   count_kernel<IdT><<<(unsigned) blocks, 256, 0, stream>>>(static_cast<const IdT*>(ids), so, si, n_inner, npix, P, counts,
-                                                           ids32, flat ? 1 : 0);
+                                                           ids32, flat ? 1 : 0, epoch);
   SMESH_LAUNCH_CHECK("count_kernel");
   return SMESH_OK;
 }
 
-static int add_view(int kind, const void* ids, int id_dtype, int64_t ids_so, int64_t ids_si, const float* probs,
-                    const float* weights, int64_t w_so, int64_t w_si, int64_t n_outer, int64_t n_inner, int C, int64_t P,
-                    float iew, uint32_t* counts, uint32_t* ids32, float* acc, cudaStream_t stream)
+static int launch_count_any(const char* fn, int id_dtype, const void* ids, int64_t so, int64_t si, int64_t n_inner,
+                            int64_t npix, int64_t P, uint32_t* counts, uint32_t* ids32, bool flat, uint32_t epoch,
+                            cudaStream_t stream)
 {
-  const int64_t npix = n_outer * n_inner;
-  if (npix == 0 || P == 0)
-  {
-    return SMESH_OK;
-  }
-  const bool ids_flat = (ids_si == 1 || n_inner == 1) && (ids_so == n_inner || n_outer == 1);
-  // 32-bit ids already in flat order are consumed in place (int32: negative values read as >= 2^31 and fail `id < P`)
-  const bool zero_copy = ids_flat && (id_dtype == SMESH_ID_U32 || (id_dtype == SMESH_ID_I32 && P <= 0x7FFFFFFFll));
-  uint32_t* ids32_out = zero_copy ? nullptr : ids32;
-  int rc;
   switch (id_dtype)
   {
-    case SMESH_ID_U32: rc = launch_count<uint32_t>(ids, ids_so, ids_si, n_inner, npix, P, counts, ids32_out, ids_flat, stream); break;
-    case SMESH_ID_I32: rc = launch_count<int32_t>(ids, ids_so, ids_si, n_inner, npix, P, counts, ids32_out, ids_flat, stream); break;
-    case SMESH_ID_U64: rc = launch_count<uint64_t>(ids, ids_so, ids_si, n_inner, npix, P, counts, ids32_out, ids_flat, stream); break;
-    case SMESH_ID_I64: rc = launch_count<int64_t>(ids, ids_so, ids_si, n_inner, npix, P, counts, ids32_out, ids_flat, stream); break;
-    default: set_error("smesh_fuse_add: unknown id dtype %d", id_dtype); return SMESH_ERR_INVALID_ARGUMENT;
+    case SMESH_ID_U32: return launch_count<uint32_t>(ids, so, si, n_inner, npix, P, counts, ids32, flat, epoch, stream);
+    case SMESH_ID_I32: return launch_count<int32_t>(ids, so, si, n_inner, npix, P, counts, ids32, flat, epoch, stream);
+    case SMESH_ID_U64: return launch_count<uint64_t>(ids, so, si, n_inner, npix, P, counts, ids32, flat, epoch, stream);
+    case SMESH_ID_I64: return launch_count<int64_t>(ids, so, si, n_inner, npix, P, counts, ids32, flat, epoch, stream);
+    default: set_error("%s: unknown id dtype %d", fn, id_dtype); return SMESH_ERR_INVALID_ARGUMENT;
   }
-  if (rc != SMESH_OK)
-  {
-    return rc;
-  }
-  const uint32_t* ids_flat_ptr = zero_copy ? static_cast<const uint32_t*>(ids) : ids32;
+}
 
-  if (weights != nullptr)
+static int check_epoch(const char* fn, uint32_t epoch, int64_t npix)
+{
+  if (epoch > 255u)
   {
-    const bool w_flat = (w_si == 1 || n_inner == 1) && (w_so == n_inner || n_outer == 1);
-    if (!w_flat)
-    {
-      set_error("smesh_fuse_add: the weights image must be contiguous in the same pixel order as the probability image");
-      return SMESH_ERR_UNSUPPORTED;
-    }
+    set_error("%s: count_epoch %u out of range (0..255)", fn, epoch);
+    return SMESH_ERR_INVALID_ARGUMENT;
   }
+  if (epoch != 0 && npix > (int64_t) COUNT_MASK)
+  {
+    set_error("%s: images of %lld pixels need count_epoch 0 (tagged counters hold 24 bits)", fn, (long long) npix);
+    return SMESH_ERR_UNSUPPORTED;
+  }
+  return SMESH_OK;
+}
 
+static ScatterArgs make_scatter_args(const uint32_t* ids32, const float* probs, const float* weights, const uint32_t* counts,
+                                     float* acc, int64_t npix, int C, int64_t P, float iew, uint32_t epoch)
+{
   ScatterArgs args;
   args.probs = probs;
-  args.ids = ids_flat_ptr;
+  args.ids = ids32;
   args.weights = weights;
   args.counts = counts;
   args.acc = acc;
@@ -642,20 +774,66 @@ static int add_view(int kind, const void* ids, int id_dtype, int64_t ids_so, int
   args.C = C;
   args.Cpad = smesh_fuse_padded_classes(C);
   args.stages = 0;
+  args.count_mask = epoch != 0 ? COUNT_MASK : 0xFFFFFFFFu;
+  args.run_cap = scatter_run_cap();
   args.iew = iew;
+  return args;
+}
+
+static int launch_scatter_kind(int kind, const ScatterArgs& args, cudaStream_t stream)
+{
   switch (kind)
   {
-    case SMESH_KIND_SUM: rc = launch_scatter<SMESH_KIND_SUM>(args, stream); break;
-    case SMESH_KIND_SUMMAX: rc = launch_scatter<SMESH_KIND_SUMMAX>(args, stream); break;
-    case SMESH_KIND_MUL: rc = launch_scatter<SMESH_KIND_MUL>(args, stream); break;
-    default: set_error("smesh_fuse_add: unknown aggregator kind %d", kind); return SMESH_ERR_INVALID_ARGUMENT;
+    case SMESH_KIND_SUM: return launch_scatter<SMESH_KIND_SUM>(args, stream);
+    case SMESH_KIND_SUMMAX: return launch_scatter<SMESH_KIND_SUMMAX>(args, stream);
+    case SMESH_KIND_MUL: return launch_scatter<SMESH_KIND_MUL>(args, stream);
+    default: set_error("unknown aggregator kind %d", kind); return SMESH_ERR_INVALID_ARGUMENT;
   }
+}
+
+static int add_view(int kind, const void* ids, int id_dtype, int64_t ids_so, int64_t ids_si, const float* probs,
+                    const float* weights, int64_t w_so, int64_t w_si, int64_t n_outer, int64_t n_inner, int C, int64_t P,
+                    float iew, uint32_t* counts, uint32_t* ids32, float* acc, uint32_t epoch, cudaStream_t stream)
+{
+  const int64_t npix = n_outer * n_inner;
+  if (npix == 0 || P == 0)
+  {
+    return SMESH_OK;
+  }
+  int rc = check_epoch("smesh_fuse_add", epoch, npix);
   if (rc != SMESH_OK)
   {
     return rc;
   }
-  clear_kernel<<<(unsigned) ((npix + 255) / 256), 256, 0, stream>>>(ids_flat_ptr, npix, P, counts);
-  SMESH_LAUNCH_CHECK("clear_kernel");
+  if (weights != nullptr)
+  {
+    const bool w_flat = (w_si == 1 || n_inner == 1) && (w_so == n_inner || n_outer == 1);
+    if (!w_flat)
+    {
+      set_error("smesh_fuse_add: the weights image must be contiguous in the same pixel order as the probability image");
+      return SMESH_ERR_UNSUPPORTED;
+    }
+  }
+  const bool ids_flat = (ids_si == 1 || n_inner == 1) && (ids_so == n_inner || n_outer == 1);
+  // 32-bit ids already in flat order are consumed in place (int32: negative values read as >= 2^31 and fail `id < P`)
+  const bool zero_copy = ids_flat && (id_dtype == SMESH_ID_U32 || (id_dtype == SMESH_ID_I32 && P <= 0x7FFFFFFFll));
+  rc = launch_count_any("smesh_fuse_add", id_dtype, ids, ids_so, ids_si, n_inner, npix, P, counts, zero_copy ? nullptr : ids32,
+                        ids_flat, epoch, stream);
+  if (rc != SMESH_OK)
+  {
+    return rc;
+  }
+  const uint32_t* ids_flat_ptr = zero_copy ? static_cast<const uint32_t*>(ids) : ids32;
+  rc = launch_scatter_kind(kind, make_scatter_args(ids_flat_ptr, probs, weights, counts, acc, npix, C, P, iew, epoch), stream);
+  if (rc != SMESH_OK)
+  {
+    return rc;
+  }
+  if (epoch == 0)
+  {
+    clear_kernel<<<(unsigned) ((npix + 255) / 256), 256, 0, stream>>>(ids_flat_ptr, npix, P, counts);
+    SMESH_LAUNCH_CHECK("clear_kernel");
+  }
   return SMESH_OK;
 }
 
@@ -695,7 +873,7 @@ extern "C" int smesh_fuse_padded_classes(int C)
 extern "C" int smesh_fuse_add(int kind, const void* ids, int id_dtype, int64_t ids_stride_outer, int64_t ids_stride_inner,
                               const float* probs, const float* weights, int64_t w_stride_outer, int64_t w_stride_inner,
                               int64_t n_outer, int64_t n_inner, int C, int64_t P, float iew, uint32_t* counts,
-                              uint32_t* ids32, float* acc, void* stream)
+                              uint32_t count_epoch, uint32_t* ids32, float* acc, void* stream)
 {
   const int rc = check_add_args("smesh_fuse_add", kind, ids, probs, n_outer, n_inner, C, P, counts, ids32, acc);
   if (rc != SMESH_OK)
@@ -703,12 +881,12 @@ extern "C" int smesh_fuse_add(int kind, const void* ids, int id_dtype, int64_t i
     return rc;
   }
   return add_view(kind, ids, id_dtype, ids_stride_outer, ids_stride_inner, probs, weights, w_stride_outer, w_stride_inner,
-                  n_outer, n_inner, C, P, iew, counts, ids32, acc, static_cast<cudaStream_t>(stream));
+                  n_outer, n_inner, C, P, iew, counts, ids32, acc, count_epoch, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int smesh_fuse_count(const void* ids, int id_dtype, int64_t ids_stride_outer, int64_t ids_stride_inner,
-                                int64_t n_outer, int64_t n_inner, int64_t P, uint32_t* counts, uint32_t* ids32_out,
-                                void* stream_v)
+                                int64_t n_outer, int64_t n_inner, int64_t P, uint32_t* counts, uint32_t count_epoch,
+                                uint32_t* ids32_out, void* stream_v)
 {
   if (n_outer < 0 || n_inner < 0 || P < 0 || P >= 0xFFFFFFFFll || (n_outer * n_inner > 0 && P > 0 && (!ids || !counts)))
   {
@@ -720,20 +898,19 @@ extern "C" int smesh_fuse_count(const void* ids, int id_dtype, int64_t ids_strid
   {
     return SMESH_OK;
   }
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  const bool flat = (ids_stride_inner == 1 || n_inner == 1) && (ids_stride_outer == n_inner || n_outer == 1);
-  switch (id_dtype)
+  const int rc = check_epoch("smesh_fuse_count", count_epoch, npix);
+  if (rc != SMESH_OK)
   {
-    case SMESH_ID_U32: return launch_count<uint32_t>(ids, ids_stride_outer, ids_stride_inner, n_inner, npix, P, counts, ids32_out, flat, stream);
-    case SMESH_ID_I32: return launch_count<int32_t>(ids, ids_stride_outer, ids_stride_inner, n_inner, npix, P, counts, ids32_out, flat, stream);
-    case SMESH_ID_U64: return launch_count<uint64_t>(ids, ids_stride_outer, ids_stride_inner, n_inner, npix, P, counts, ids32_out, flat, stream);
-    case SMESH_ID_I64: return launch_count<int64_t>(ids, ids_stride_outer, ids_stride_inner, n_inner, npix, P, counts, ids32_out, flat, stream);
-    default: set_error("smesh_fuse_count: unknown id dtype %d", id_dtype); return SMESH_ERR_INVALID_ARGUMENT;
+    return rc;
   }
+  const bool flat = (ids_stride_inner == 1 || n_inner == 1) && (ids_stride_outer == n_inner || n_outer == 1);
+  return launch_count_any("smesh_fuse_count", id_dtype, ids, ids_stride_outer, ids_stride_inner, n_inner, npix, P, counts,
+                          ids32_out, flat, count_epoch, static_cast<cudaStream_t>(stream_v));
 }
 
 extern "C" int smesh_fuse_scatter(int kind, const uint32_t* ids32, const float* probs, const float* weights, int64_t n_pix,
-                                  int C, int64_t P, float iew, const uint32_t* counts, float* acc, void* stream_v)
+                                  int C, int64_t P, float iew, const uint32_t* counts, uint32_t count_epoch, float* acc,
+                                  void* stream_v)
 {
   if (n_pix < 0 || C < 1 || P < 0 || kind < 0 || kind > 2 || (n_pix > 0 && P > 0 && (!ids32 || !probs || !counts || !acc)))
   {
@@ -749,26 +926,13 @@ extern "C" int smesh_fuse_scatter(int kind, const uint32_t* ids32, const float* 
   {
     return SMESH_OK;
   }
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  ScatterArgs args;
-  args.probs = probs;
-  args.ids = ids32;
-  args.weights = weights;
-  args.counts = counts;
-  args.acc = acc;
-  args.npix = n_pix;
-  args.P = P;
-  args.ntiles = 0;
-  args.C = C;
-  args.Cpad = smesh_fuse_padded_classes(C);
-  args.stages = 0;
-  args.iew = iew;
-  switch (kind)
+  const int rc = check_epoch("smesh_fuse_scatter", count_epoch, n_pix);
+  if (rc != SMESH_OK)
   {
-    case SMESH_KIND_SUM: return launch_scatter<SMESH_KIND_SUM>(args, stream);
-    case SMESH_KIND_SUMMAX: return launch_scatter<SMESH_KIND_SUMMAX>(args, stream);
-    default: return launch_scatter<SMESH_KIND_MUL>(args, stream);
+    return rc;
   }
+  return launch_scatter_kind(kind, make_scatter_args(ids32, probs, weights, counts, acc, n_pix, C, P, iew, count_epoch),
+                             static_cast<cudaStream_t>(stream_v));
 }
 
 extern "C" int smesh_fuse_clear(const uint32_t* ids32, int64_t n_pix, int64_t P, uint32_t* counts, void* stream_v)
@@ -791,16 +955,18 @@ extern "C" int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id
                                     int64_t ids_stride_outer, int64_t ids_stride_inner, const float* probs,
                                     int64_t probs_stride_view, const float* weights, int64_t w_stride_view,
                                     int64_t w_stride_outer, int64_t w_stride_inner, int64_t n_outer, int64_t n_inner, int C,
-                                    int64_t P, float iew, uint32_t* counts, uint32_t* ids32, float* acc, void* stream)
+                                    int64_t P, float iew, uint32_t* counts, uint32_t count_epoch0, uint32_t* ids32, float* acc,
+                                    void* stream)
 {
   int rc = check_add_args("smesh_fuse_add_batch", kind, ids, probs, n_outer, n_inner, C, P, counts, ids32, acc);
   if (rc != SMESH_OK)
   {
     return rc;
   }
-  if (B < 0)
+  if (B < 0 || (count_epoch0 != 0 && (int64_t) count_epoch0 + B - 1 > 255))
   {
-    set_error("smesh_fuse_add_batch: negative batch size");
+    set_error("smesh_fuse_add_batch: invalid batch (B=%lld, count_epoch0=%u: epochs must stay <= 255)", (long long) B,
+              count_epoch0);
     return SMESH_ERR_INVALID_ARGUMENT;
   }
   const size_t id_size = (id_dtype == SMESH_ID_U64 || id_dtype == SMESH_ID_I64) ? 8 : 4;
@@ -810,7 +976,8 @@ extern "C" int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id
     const float* probs_b = probs + (size_t) b * probs_stride_view;
     const float* weights_b = weights ? weights + (size_t) b * w_stride_view : nullptr;
     rc = add_view(kind, ids_b, id_dtype, ids_stride_outer, ids_stride_inner, probs_b, weights_b, w_stride_outer,
-                  w_stride_inner, n_outer, n_inner, C, P, iew, counts, ids32, acc, static_cast<cudaStream_t>(stream));
+                  w_stride_inner, n_outer, n_inner, C, P, iew, counts, ids32, acc,
+                  count_epoch0 != 0 ? count_epoch0 + (uint32_t) b : 0u, static_cast<cudaStream_t>(stream));
     if (rc != SMESH_OK)
     {
       return rc;

@@ -11,21 +11,23 @@ KIND = {"sum": 0, "summax": 1, "mul": 2}
 ID_U32, ID_I32, ID_U64, ID_I64 = 0, 1, 2, 3
 
 _vp, _i64, _int, _f32, _sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+_u32 = ctypes.c_uint32
 
 # every symbol include/smesh.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "smesh_last_error": (ctypes.c_char_p, []),
     "smesh_version": (ctypes.c_char_p, []),
     "smesh_raster_workspace_bytes": (_int, [_i64, _i64, _int, _int, ctypes.POINTER(_sz)]),
-    "smesh_raster_render": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _vp, _vp, _vp]),
+    "smesh_raster_face_flags": (_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "smesh_raster_render": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _vp, _vp, _vp]),
     "smesh_fuse_padded_classes": (_int, [_int]),
-    "smesh_fuse_add": (_int, [_int, _vp, _int, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _int, _i64, _f32, _vp, _vp,
-                              _vp, _vp]),
-    "smesh_fuse_count": (_int, [_vp, _int, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
-    "smesh_fuse_scatter": (_int, [_int, _vp, _vp, _vp, _i64, _int, _i64, _f32, _vp, _vp, _vp]),
+    "smesh_fuse_add": (_int, [_int, _vp, _int, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _int, _i64, _f32, _vp, _u32,
+                              _vp, _vp, _vp]),
+    "smesh_fuse_count": (_int, [_vp, _int, _i64, _i64, _i64, _i64, _i64, _vp, _u32, _vp, _vp]),
+    "smesh_fuse_scatter": (_int, [_int, _vp, _vp, _vp, _i64, _int, _i64, _f32, _vp, _u32, _vp, _vp]),
     "smesh_fuse_clear": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "smesh_fuse_add_batch": (_int, [_int, _i64, _vp, _int, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64,
-                                    _int, _i64, _f32, _vp, _vp, _vp, _vp]),
+                                    _int, _i64, _f32, _vp, _u32, _vp, _vp, _vp]),
     "smesh_fuse_get": (_int, [_int, _vp, _i64, _int, _vp, _vp]),
 }
 

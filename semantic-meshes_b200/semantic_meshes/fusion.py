@@ -52,6 +52,7 @@ class MeshAggregator:
         self._acc = torch.zeros((primitives, self._cpad), dtype=torch.float32, device=self.device)
         self._counts = torch.zeros((max(primitives, 1),), dtype=torch.int32, device=self.device)
         self._ids32 = torch.empty((0,), dtype=torch.int32, device=self.device)
+        self._epoch = 0  # last count epoch handed out (see include/smesh.h: tagged per-view pixel counters)
 
     # ---------------------------------------------------------------------------------------------------------------
     def _as_tensor(self, obj, what):
@@ -127,6 +128,25 @@ class MeshAggregator:
                 w_so, w_si = n_inner, 1
         return pr, wt, n_outer, n_inner, ids_so, ids_si, w_so, w_si
 
+    def restart_epochs(self):
+        """Zero the per-view pixel counters and start the count epochs over. Called automatically when the 8-bit epoch
+        wraps; call it yourself at the start of any region you capture into a CUDA graph, so every replay sees the same
+        epochs on clean counters."""
+        self._counts.zero_()
+        self._epoch = 0
+
+    def _next_epochs(self, npix, n=1):
+        """-> first of n consecutive count epochs for views of npix pixels (0 = untagged mode for huge images)."""
+        if npix >= (1 << 24):
+            if self._epoch != 0:
+                self.restart_epochs()
+            return 0
+        if self._epoch + n > 255:
+            self.restart_epochs()
+        first = self._epoch + 1
+        self._epoch += n
+        return first
+
     def _scratch(self, npix):
         if self._ids32.numel() < npix:
             self._ids32 = self._torch.empty((npix,), dtype=self._torch.int32, device=self.device)
@@ -145,8 +165,9 @@ class MeshAggregator:
             rc = _lib.lib.smesh_fuse_add(self._kind, ids.data_ptr(), id_dtype, ids_so, ids_si, pr.data_ptr(),
                                          wt.data_ptr() if wt is not None else None, w_so, w_si, n_outer, n_inner,
                                          self.classes, self.primitives, self.images_equal_weight,
-                                         self._counts.data_ptr(), self._scratch(n_outer * n_inner).data_ptr(),
-                                         self._acc.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                                         self._counts.data_ptr(), self._next_epochs(n_outer * n_inner),
+                                         self._scratch(n_outer * n_inner).data_ptr(), self._acc.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream)
         _lib.check(rc)
 
     def add_batch(self, primitive_indices, probs, weights=None):
@@ -171,14 +192,20 @@ class MeshAggregator:
             for b in range(B):  # layouts that need a copy: go view by view
                 self.add(ids[b], pr[b], wt[b] if wt is not None else None)
             return
-        with torch.cuda.device(self.device):
-            rc = _lib.lib.smesh_fuse_add_batch(self._kind, B, ids.data_ptr(), id_dtype, ids.stride(0), ids_so, ids_si,
-                                               pr.data_ptr(), pr.stride(0), wt.data_ptr() if wt is not None else None,
-                                               wt.stride(0) if wt is not None else 0, w_so, w_si, n_outer, n_inner,
-                                               self.classes, self.primitives, self.images_equal_weight,
-                                               self._counts.data_ptr(), self._scratch(n_outer * n_inner).data_ptr(),
-                                               self._acc.data_ptr(), torch.cuda.current_stream().cuda_stream)
-        _lib.check(rc)
+        npix = n_outer * n_inner
+        done = 0
+        while done < B:
+            nb = min(B - done, 255)
+            epoch0 = self._next_epochs(npix, nb)
+            with torch.cuda.device(self.device):
+                rc = _lib.lib.smesh_fuse_add_batch(
+                    self._kind, nb, ids[done].data_ptr(), id_dtype, ids.stride(0), ids_so, ids_si, pr[done].data_ptr(),
+                    pr.stride(0), wt[done].data_ptr() if wt is not None else None, wt.stride(0) if wt is not None else 0,
+                    w_so, w_si, n_outer, n_inner, self.classes, self.primitives, self.images_equal_weight,
+                    self._counts.data_ptr(), epoch0, self._scratch(npix).data_ptr(), self._acc.data_ptr(),
+                    torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc)
+            done += nb
 
     def reset(self):
         """ModelAggregator::reset (Mesh.h:119-122): every row back to the aggregator's zero (mul: -log 1 = 0)."""

@@ -31,6 +31,12 @@ class TriangleRenderer:
         # what TriangleRenderer's ctor uploads (TriangleRenderer.h:30-39)
         self._verts = torch.from_numpy(verts).to(self.device)
         self._faces = torch.from_numpy(faces).to(self.device)
+        # per-face "well shaped" flags: lets the kernel skip triangles far outside the image (include/smesh.h)
+        self._face_flags = torch.zeros((max(self._F, 1),), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.smesh_raster_face_flags(self._verts.data_ptr(), self._V, self._faces.data_ptr(), self._F,
+                                                        self._face_flags.data_ptr(),
+                                                        torch.cuda.current_stream().cuda_stream))
         self._workspace = None
         self._workspace_res = None
 
@@ -41,7 +47,7 @@ class TriangleRenderer:
         if self._workspace_res != (W, H):
             nbytes = ctypes.c_size_t(0)
             _lib.check(_lib.lib.smesh_raster_workspace_bytes(self._V, self._F, W, H, ctypes.byref(nbytes)))
-            self._workspace = self._torch.empty(nbytes.value, dtype=self._torch.uint8, device=self.device)
+            self._workspace = self._torch.zeros(nbytes.value, dtype=self._torch.uint8, device=self.device)
             self._workspace_res = (W, H)
         return self._workspace
 
@@ -66,7 +72,7 @@ class TriangleRenderer:
             R, t = camera.rotation, camera.translation
             f, c = camera.focal_lengths, camera.principal_point
             rc = _lib.lib.smesh_raster_render(self._verts.data_ptr(), self._V, self._faces.data_ptr(), self._F,
-                                              R.ctypes.data, t.ctypes.data, f.ctypes.data, c.ctypes.data, W, H,
+                                              self._face_flags.data_ptr(), R.ctypes.data, t.ctypes.data, f.ctypes.data, c.ctypes.data, W, H,
                                               ws.data_ptr(), ws.numel(), idx.data_ptr(), depth.data_ptr(),
                                               torch.cuda.current_stream().cuda_stream)
         _lib.check(rc)

@@ -33,16 +33,16 @@ def test_workspace_bytes_and_errors():
     from semantic_meshes import _lib
     n = ctypes.c_size_t(0)
     assert _lib.lib.smesh_raster_workspace_bytes(642, 1280, 256, 256, ctypes.byref(n)) == 0
-    assert n.value >= 642 * 16 + 256 * 256 * 8 + 1280 * 4
+    assert n.value >= 642 * 16 + 256 * 256 * 12 + 1280 * 4
     assert _lib.lib.smesh_raster_workspace_bytes(10, 10, 0, 5, ctypes.byref(n)) == _lib.ERR_INVALID_ARGUMENT
     assert b"invalid argument" in _lib.lib.smesh_last_error()
     with pytest.raises(ValueError):
         _lib.check(_lib.ERR_INVALID_ARGUMENT)
     # argument checks happen before any CUDA call
-    assert _lib.lib.smesh_fuse_add(7, None, 0, 0, 0, None, None, 0, 0, 4, 4, 3, 10, 0.5, None, None, None, None) \
+    assert _lib.lib.smesh_fuse_add(7, None, 0, 0, 0, None, None, 0, 0, 4, 4, 3, 10, 0.5, None, 1, None, None, None) \
         == _lib.ERR_INVALID_ARGUMENT
     assert _lib.lib.smesh_fuse_get(0, None, 5, 0, None, None) == _lib.ERR_INVALID_ARGUMENT
-    assert _lib.lib.smesh_raster_render(None, 0, None, 0, None, None, None, None, 4, 4, None, 0, None, None, None) \
+    assert _lib.lib.smesh_raster_render(None, 0, None, 0, None, None, None, None, None, 4, 4, None, 0, None, None, None) \
         == _lib.ERR_INVALID_ARGUMENT
 
 

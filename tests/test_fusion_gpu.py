@@ -70,8 +70,6 @@ def test_parity_with_oracle(sm, kind, C, iew):
         ref.add(ids, probs, wts)
     assert_acc_close(kind, agg.state().cpu().numpy(), ref.acc)
     assert_get_close(kind, agg.get(), ref.get())
-    # counters are handed back clean for the next view
-    assert not agg._counts.any().item()
     agg.reset()
     assert not agg.state().any().item()
 
@@ -220,6 +218,28 @@ def test_error_behaviour(sm):
         sm.fusion.MeshAggregator(P, C, aggregator="median")
     sm.fusion.MeshAggregator(P, C, aggregator="Sum")  # first letter is case-insensitive (Fusion.cu:126)
     sm.fusion.MeshAggregator(primitives=P, classes=C, aggregator="mul", images_equal_weight=0.25)
+
+
+def test_count_epoch_wraparound(sm):
+    """The per-view pixel counters are tagged with an 8-bit epoch instead of being cleared (include/smesh.h); 600 views
+    cross the wrap twice, and the face -> pixel-count mapping changes every view."""
+    import torch
+    rng = np.random.default_rng(33)
+    W, H, C, P = 16, 12, 3, 20
+    agg, ref = sm.fusion.MeshAggregator(P, C), oracle.Aggregator(P, C)
+    views = [make_view(rng, W, H, C, P, block=1 + (v % 3)) for v in range(12)]
+    dev = [(torch.from_numpy(i.view(np.int32)).cuda(), torch.from_numpy(p).cuda()) for i, p in views]
+    for v in range(600):
+        agg.add(*dev[v % 12])
+        ref.add(*views[v % 12])
+    assert_acc_close("sum", agg.state().cpu().numpy(), ref.acc, rtol=2e-5)
+    # batches are split at the wrap as well
+    ids = torch.stack([d[0] for d in dev] * 30)
+    probs = torch.stack([d[1] for d in dev] * 30)
+    agg.add_batch(ids, probs)
+    for v in range(360):
+        ref.add(*views[v % 12])
+    assert_acc_close("sum", agg.state().cpu().numpy(), ref.acc, rtol=2e-5)
 
 
 def test_add_batch_equals_sequential(sm):

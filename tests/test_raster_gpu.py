@@ -93,6 +93,53 @@ def test_large_triangles_and_ties(sm):
     assert set(np.unique(gi)) <= {0, 2, BG} and (gi == 0).any() and (gi == 2).any()
 
 
+def test_offscreen_drop_is_exact(sm):
+    """Triangles far outside the image are dropped without testing when that provably cannot change the result
+    (smesh_raster.cu far_offscreen()). A soup of random triangles scattered around and beyond all four image borders -
+    well shaped ones, needles, slivers crossing the border, some behind the camera - must still match the oracle, which
+    tests every bounding-box pixel like the reference."""
+    from semantic_meshes.data import Camera, Ply
+    rng = np.random.default_rng(123)
+    W, H, f = 200, 120, 150.0
+    n = 6000
+    z = rng.uniform(0.5, 6.0, (n, 1))
+    # projected centre anywhere in [-0.6 W, 1.6 W] x [-0.6 H, 1.6 H]
+    cx = rng.uniform(-0.6 * W, 1.6 * W, (n, 1))
+    cy = rng.uniform(-0.6 * H, 1.6 * H, (n, 1))
+    centre = np.concatenate([(cx - W / 2) * z / f, (cy - H / 2) * z / f, z], axis=1)
+    size = rng.choice([0.02, 0.1, 0.5, 2.0], (n, 1, 1))
+    offs = rng.normal(size=(n, 3, 3)) * size
+    needle = rng.random(n) < 0.2
+    offs[needle, 2] = offs[needle, 1] * (1 + 1e-3 * rng.normal(size=(needle.sum(), 1)))   # nearly collinear
+    verts = (centre[:, None, :] + offs).reshape(-1, 3).astype(np.float32)
+    verts[rng.random(verts.shape[0]) < 0.02, 2] *= -1                                   # a few vertices behind
+    faces = np.arange(3 * n, dtype=np.int32).reshape(n, 3)
+    mesh = Ply.from_arrays(verts, faces)
+    renderer = sm.render.triangles(mesh)
+    flags = renderer._face_flags.cpu().numpy()[:n]
+    assert 0.5 < flags.mean() < 0.9                      # needles are not "well shaped", the rest is
+    for shift in (0.0, 0.37):
+        cam = Camera(np.eye(3), np.array([shift, -shift, 0.0]), np.array([W, H]), np.array([f, f]),
+                     np.array([W / 2, H / 2]))
+        gi, gd, oi, od = render_both(sm, mesh, cam, renderer)
+        assert_bit_exact(gi, gd, oi, od)
+        assert (gi != BG).mean() > 0.3
+
+
+def test_intrinsics_change_rebuilds_ray_table(sm):
+    """The per-pixel ray normalisation is cached per intrinsics inside the renderer's workspace."""
+    from semantic_meshes import synthetic
+    from semantic_meshes.data import Camera
+    mesh = synthetic.mesh("icosphere")
+    renderer = sm.render.triangles(mesh)
+    W, H = 120, 90
+    R, t = synthetic.look_at(np.array([0.0, -3.0, 0.5]), np.zeros(3))
+    for f, c in ((100.0, (60.0, 45.0)), (140.0, (60.0, 45.0)), (140.0, (50.5, 40.25)), (100.0, (60.0, 45.0))):
+        cam = Camera(R, t, np.array([W, H]), np.array([f, f * 1.01]), np.array(c))
+        gi, gd, oi, od = render_both(sm, mesh, cam, renderer)
+        assert_bit_exact(gi, gd, oi, od)
+
+
 def test_deterministic_and_capsule(sm):
     import torch
     from semantic_meshes import synthetic

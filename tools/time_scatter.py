@@ -1,0 +1,33 @@
+"""GPU box: time the scatter kernel alone on one bench config (used with SMESH_SCATTER_NW / SMESH_SCATTER_STAGES)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "semantic-meshes_b200")]
+import numpy as np, torch
+import semantic_meshes
+from semantic_meshes import synthetic, _lib
+import bench
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+cfg = bench.CONFIGS[name]
+W, H, C = cfg["W"], cfg["H"], cfg["C"]
+mesh, cams = bench.build_scene(cfg, 0, B)
+renderer = semantic_meshes.render.triangles(mesh)
+P = renderer.getPrimitivesNum()
+agg = semantic_meshes.fusion.MeshAggregator(P, C)
+probs = [synthetic.predictions_torch(W, H, C, seed=b, device="cuda") for b in range(B)]
+ids = [renderer.render(cams[b])[0] for b in range(B)]
+stream = torch.cuda.current_stream().cuda_stream
+ev = []
+for rep in range(6):
+    agg.restart_epochs()
+    for b in range(B):
+        _lib.check(_lib.lib.smesh_fuse_count(ids[b].data_ptr(), _lib.ID_I32, H, 1, W, H, P, agg._counts.data_ptr(), b + 1, None, stream))
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        _lib.check(_lib.lib.smesh_fuse_scatter(0, ids[b].data_ptr(), probs[b].data_ptr(), None, W * H, C, P, 0.5, agg._counts.data_ptr(), b + 1, agg._acc.data_ptr(), stream))
+        e1.record()
+        if rep > 0:
+            ev.append((e0, e1))
+torch.cuda.synchronize()
+t = np.array([a.elapsed_time(b) for a, b in ev]) * 1e3
+print(f"{name} NW={os.environ.get('SMESH_SCATTER_NW','-')} ST={os.environ.get('SMESH_SCATTER_STAGES','-')}: scatter {t.mean():.1f} us (min {t.min():.1f}, max {t.max():.1f}); input-only {(4*W*H*(C+1))/t.mean()/1e3:.0f} GB/s")
