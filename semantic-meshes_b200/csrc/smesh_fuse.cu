@@ -234,6 +234,7 @@ struct ScatterArgs
   int stages;
   uint32_t count_mask;     // COUNT_MASK with a tagged epoch, 0xFFFFFFFF without
   uint32_t run_cap;        // power of two <= 32: runs of equal ids are cut every run_cap lanes
+  uint32_t debug_skip;     // profiling only: 1 = no reductions, 2 = no run reduction, 4 = no per-pixel work at all
   float iew;
 };
 
@@ -520,6 +521,328 @@ __global__ void __launch_bounds__(288) scatter_kernel(ScatterArgs a)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 2'. scatter, narrow class vectors (compile-time C <= 20): TWO adjacent pixels per lane.
+//
+// Same ring, same arithmetic per pixel; a consumer warp owns 64 consecutive pixels of a stage and lane l holds pixels
+// A = 2l and B = 2l+1 in registers (their 2C floats are contiguous and 8-byte aligned: C 64-bit shared loads, conflict
+// free). Equal-id neighbours A, B are added in registers first, so the shuffle rounds of the run reduction work on lanes
+// that already hold two pixels: about half the shuffles, half the instructions and half the reductions' bookkeeping per
+// pixel compared to scatter_kernel. Bookkeeping per lane:
+//   S = the part of the lane that belongs to the run entering from the LEFT (A, or A + B when merged)
+//   T = B when B starts a new run inside the lane (split lane)
+// S-chains are reduced towards their leftmost lane with a segmented suffix scan over lanes; a split lane then adds the
+// finished chain of its right neighbour to T. Run heads (S or T) issue the 128-bit reductions.
+// ---------------------------------------------------------------------------------------------------------------------
+
+template <int KIND, int CT, bool TMA_FLUSH>
+__global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
+{
+  static_assert(CT >= 1 && CT <= CH, "pair kernel holds 2 x CT values in registers");
+  constexpr int C = CT;
+  constexpr int Cpad = (CT + 3) & ~3;
+  constexpr int NCHUNK = Cpad / 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int NW = (int) (blockDim.x >> 5) - 1;
+  const int tile_px = NW * 64;
+  const size_t stage_floats = (size_t) tile_px * C;
+  const int stages = a.stages;
+
+  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + stage_floats * stages);
+  uint64_t* empty_bar = full_bar + stages;
+  // TMA_FLUSH: per consumer warp 2 x 32 row slots of Cpad floats (run sums staged for cp.reduce.async.bulk)
+  float* flush_base = reinterpret_cast<float*>(empty_bar + stages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0)
+  {
+    for (int s = 0; s < stages; s++)
+    {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, (uint32_t) NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0)
+  {
+    if (lane == 0)
+    {
+      const uint64_t policy = l2_evict_first_policy();
+      int s = 0;
+      uint32_t use_parity = 1;
+      bool first_pass = true;
+      for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
+      {
+        if (!first_pass)
+        {
+          mbar_wait(empty_bar + s, use_parity);
+        }
+        const int64_t px0 = tile * tile_px;
+        const int64_t px_n = min((int64_t) tile_px, a.npix - px0);
+        const size_t nfloats = (size_t) px_n * C;
+        const uint32_t bulk_bytes = (uint32_t) ((nfloats * 4) & ~(size_t) 15);
+        float* dst = stage_base + stage_floats * s;
+        const float* src = a.probs + (size_t) px0 * C;
+        for (size_t k = bulk_bytes / 4; k < nfloats; k++)
+        {
+          dst[k] = src[k];
+        }
+        mbar_arrive_expect_tx(full_bar + s, bulk_bytes);
+        if (bulk_bytes > 0)
+        {
+          bulk_g2s(dst, src, bulk_bytes, full_bar + s, policy);
+        }
+        if (++s == stages)
+        {
+          s = 0;
+          first_pass = false;
+          use_parity ^= 1u;
+        }
+      }
+    }
+    return;
+  }
+
+  const int cw = warp - 1;
+  const int64_t lane_px = (int64_t) cw * 64 + 2 * lane; // first of this lane's two pixels inside a tile
+  const int64_t tile_stride = gridDim.x;
+  const uint32_t P32 = (uint32_t) a.P;
+  const bool has_weights = a.weights != nullptr;
+
+  // side inputs (L2 gathers) are fetched two tiles ahead (ids, weights) / one tile ahead (counts, which need the ids)
+  auto load_ids = [&](int64_t t) -> uint2 {
+    const int64_t i = t * tile_px + lane_px;
+    uint2 r = make_uint2(INVALID_ID, INVALID_ID);
+    if (i + 1 < a.npix)
+    {
+      r = __ldg(reinterpret_cast<const uint2*>(a.ids + i)); // i is even and the id image is 8-byte aligned (checked on host)
+    }
+    else if (i < a.npix)
+    {
+      r.x = __ldg(a.ids + i);
+    }
+    return r;
+  };
+  auto load_wts = [&](int64_t t) -> float2 {
+    const int64_t i = t * tile_px + lane_px;
+    float2 r = make_float2(1.0f, 1.0f);
+    if (has_weights)
+    {
+      if (i < a.npix) r.x = __ldg(a.weights + i);
+      if (i + 1 < a.npix) r.y = __ldg(a.weights + i + 1);
+    }
+    return r;
+  };
+  auto load_n = [&](uint32_t pid) -> uint32_t { return pid < P32 ? __ldg(a.counts + pid) : 1u; };
+
+  int64_t tile = blockIdx.x;
+  uint2 id = load_ids(tile), id1 = load_ids(tile + tile_stride);
+  float2 wt = load_wts(tile), wt1 = load_wts(tile + tile_stride);
+  uint2 n = make_uint2(load_n(id.x), load_n(id.y));
+
+  int s = 0;
+  uint32_t parity = 0;
+  const float* stage_ptr = stage_base + (size_t) lane_px * C;
+  for (; tile < a.ntiles; tile += tile_stride)
+  {
+    const uint2 id2 = load_ids(tile + 2 * tile_stride);
+    const float2 wt2 = load_wts(tile + 2 * tile_stride);
+    const uint2 n1 = make_uint2(load_n(id1.x), load_n(id1.y));
+
+    mbar_wait(full_bar + s, parity);
+    const float2* row2 = reinterpret_cast<const float2*>(stage_ptr + stage_floats * s);
+    if (a.debug_skip & 4u)
+    {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar + s);
+      if (++s == stages) { s = 0; parity ^= 1u; }
+      id = id1; id1 = id2; wt = wt1; wt1 = wt2; n = n1;
+      continue;
+    }
+
+    // ---- both pixels' class vectors: 2C contiguous floats, C 64-bit loads ----
+    float ab[2 * C];
+#pragma unroll
+    for (int k = 0; k < C; k++)
+    {
+      const float2 t = row2[k];
+      ab[2 * k] = t.x;
+      ab[2 * k + 1] = t.y;
+    }
+    float A[CH], B[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k++)
+    {
+      A[k] = k < C ? ab[k] : 0.0f;
+      B[k] = k < C ? ab[C + k] : 0.0f;
+    }
+    // ---- gate (Mesh.h:95-98): sequential float sum of each class vector > 0.5 ----
+    float sumA = 0.0f, sumB = 0.0f;
+#pragma unroll
+    for (int k = 0; k < C; k++)
+    {
+      sumA = __fadd_rn(sumA, A[k]);
+      sumB = __fadd_rn(sumB, B[k]);
+    }
+    const bool okA = id.x < P32 && sumA > 0.5f;
+    const bool okB = id.y < P32 && sumB > 0.5f;
+    const float wA = pixel_weight(a.iew, n.x & a.count_mask, wt.x);
+    const float wB = pixel_weight(a.iew, n.y & a.count_mask, wt.y);
+#pragma unroll
+    for (int k = 0; k < CH; k++)
+    {
+      if (KIND == SMESH_KIND_SUM)
+      {
+        A[k] = __fmul_rn(A[k], wA); // weighted::sum (tt/aggregator/MiscOps.h:83-93): acc += probs * w
+        B[k] = __fmul_rn(B[k], wB);
+      }
+      else
+      {
+        A[k] = (k < C && okA) ? neg_log_pow(A[k], wA) : 0.0f;
+        B[k] = (k < C && okB) ? neg_log_pow(B[k], wB) : 0.0f;
+      }
+    }
+
+    // ---- run structure ----
+    const uint32_t keyA = okA ? id.x : INVALID_ID, keyB = okB ? id.y : INVALID_ID;
+    const bool merged = okA && okB && id.x == id.y;
+    const bool hasT = okB && !merged;
+    if (merged)
+    {
+#pragma unroll
+      for (int k = 0; k < CH; k++)
+      {
+        A[k] = __fadd_rn(A[k], B[k]); // S = A + B
+      }
+    }
+    const uint32_t keyR = merged ? id.x : keyB;                       // id of the run leaving the lane on the right
+    const uint32_t keyA_next = __shfl_down_sync(0xFFFFFFFFu, keyA, 1);  // lane + 1's left pixel
+    const uint32_t keyR_prev = __shfl_up_sync(0xFFFFFFFFu, keyR, 1);    // lane - 1's right pixel
+    const bool joins_next = lane < 31 && keyR != INVALID_ID && keyA_next == keyR;
+    const bool contS = merged && joins_next;    // the S chain continues into lane + 1
+    const bool contT = hasT && joins_next;      // T (= B) is the head of a run that continues into lane + 1
+    const bool absorbed = lane > 0 && okA && keyR_prev == keyA; // A belongs to a run whose head is further left
+    const bool headS = okA && !absorbed;
+    const uint32_t contmask = __ballot_sync(0xFFFFFFFFu, contS);
+    const uint32_t stop = ~contmask & ~((1u << lane) - 1u);           // first lane >= this one whose S chain stops
+    const int end = __ffs(stop);                                        // = that lane + 1 (lane 31 never continues)
+    const int maxlen = (int) __reduce_max_sync(0xFFFFFFFFu, (unsigned) (end - lane));
+
+    // segmented suffix sum of S over the chain (log2(longest chain) shuffle rounds, warp-uniform)
+    for (int d = 1; d < ((a.debug_skip & 2u) ? 0 : maxlen); d <<= 1)
+    {
+      const bool take = lane + d < end;
+#pragma unroll
+      for (int k = 0; k < CH; k++)
+      {
+        const float t = __shfl_down_sync(0xFFFFFFFFu, A[k], d);
+        if (take)
+        {
+          A[k] = __fadd_rn(A[k], t);
+        }
+      }
+    }
+    // a split lane's B heads the run whose remainder is the finished chain of lane + 1
+    if (__any_sync(0xFFFFFFFFu, contT))
+    {
+#pragma unroll
+      for (int k = 0; k < CH; k++)
+      {
+        const float t = __shfl_down_sync(0xFFFFFFFFu, A[k], 1);
+        if (contT)
+        {
+          B[k] = __fadd_rn(B[k], t);
+        }
+      }
+    }
+    // run heads own the sums and add them to the padded accumulator row (Cpad floats, 16-byte aligned)
+    if constexpr (TMA_FLUSH)
+    {
+      // staged in shared memory and handed to the TMA unit as ONE reduce-add of the whole row per run: the L2 sees
+      // full-sector requests instead of five 16-byte ones, and the LSU is not involved
+      float* slotS = flush_base + ((size_t) cw * 64 + lane) * Cpad;
+      float* slotT = slotS + 32 * Cpad;
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // this lane's previous rows have been read
+      const bool doS = headS && !(a.debug_skip & 1u), doT = hasT && !(a.debug_skip & 1u);
+      if (doS)
+      {
+#pragma unroll
+        for (int j = 0; j < NCHUNK; j++)
+        {
+          *reinterpret_cast<float4*>(slotS + 4 * j) = make_float4(A[4 * j], A[4 * j + 1], A[4 * j + 2], A[4 * j + 3]);
+        }
+      }
+      if (doT)
+      {
+#pragma unroll
+        for (int j = 0; j < NCHUNK; j++)
+        {
+          *reinterpret_cast<float4*>(slotT + 4 * j) = make_float4(B[4 * j], B[4 * j + 1], B[4 * j + 2], B[4 * j + 3]);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (doS)
+      {
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(
+                       a.acc + (size_t) id.x * Cpad),
+                     "r"(smem_u32(slotS)), "n"(Cpad * 4)
+                     : "memory");
+      }
+      if (doT)
+      {
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(
+                       a.acc + (size_t) id.y * Cpad),
+                     "r"(smem_u32(slotT)), "n"(Cpad * 4)
+                     : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    else
+    {
+      // one 128-bit reduction per 4 classes
+      if (headS && !(a.debug_skip & 1u))
+      {
+        float* dst = a.acc + (size_t) id.x * Cpad;
+#pragma unroll
+        for (int j = 0; j < NCHUNK; j++)
+        {
+          red_add_v4(dst + 4 * j, A[4 * j], A[4 * j + 1], A[4 * j + 2], A[4 * j + 3]);
+        }
+      }
+      if (hasT && !(a.debug_skip & 1u))
+      {
+        float* dst = a.acc + (size_t) id.y * Cpad;
+#pragma unroll
+        for (int j = 0; j < NCHUNK; j++)
+        {
+          red_add_v4(dst + 4 * j, B[4 * j], B[4 * j + 1], B[4 * j + 2], B[4 * j + 3]);
+        }
+      }
+    }
+
+    __syncwarp();
+    if (lane == 0)
+    {
+      mbar_arrive(empty_bar + s);
+    }
+    if (++s == stages)
+    {
+      s = 0;
+      parity ^= 1u;
+    }
+    id = id1; id1 = id2;
+    wt = wt1; wt1 = wt2;
+    n = n1;
+  }
+  if constexpr (TMA_FLUSH)
+  {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
 // Fallback for shapes the ring cannot take (class vector too wide for shared memory, misaligned probability image):
 // one thread per pixel straight from global memory. Same arithmetic, no staging.
 template <int KIND>
@@ -693,13 +1016,83 @@ static int launch_scatter_ring(const ScatterArgs& args_in, const RingConfig& cfg
   return SMESH_OK;
 }
 
+struct PairConfig
+{
+  int consumer_warps;
+  int stages;
+};
+
+static PairConfig pair_config()
+{
+  PairConfig cfg = {4, 2};
+  static const int env_nw = getenv("SMESH_PAIR_NW") ? atoi(getenv("SMESH_PAIR_NW")) : 0;
+  static const int env_stages = getenv("SMESH_PAIR_STAGES") ? atoi(getenv("SMESH_PAIR_STAGES")) : 0;
+  if (env_nw >= 1 && env_nw <= 8) cfg.consumer_warps = env_nw;
+  if (env_stages >= 2 && env_stages <= 8) cfg.stages = env_stages;
+  return cfg;
+}
+
+template <int KIND, int CT, bool TMA_FLUSH>
+static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
+{
+  ScatterArgs args = args_in;
+  const PairConfig cfg = pair_config();
+  const size_t smem = (size_t) cfg.stages * cfg.consumer_warps * 64 * CT * 4 + (size_t) cfg.stages * 16 +
+                      (TMA_FLUSH ? (size_t) cfg.consumer_warps * 64 * ((CT + 3) & ~3) * 4 : 0);
+  auto kernel = scatter_pair_kernel<KIND, CT, TMA_FLUSH>;
+  static thread_local size_t configured_smem = 0;
+  static thread_local int blocks_per_sm = 0;
+  static thread_local int configured_threads = 0;
+  static thread_local int configured_device = -1;
+  const int threads = (cfg.consumer_warps + 1) * 32;
+  int device = 0;
+  SMESH_CUDA_CHECK(cudaGetDevice(&device));
+  if (configured_smem != smem || configured_threads != threads || configured_device != device)
+  {
+    SMESH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    SMESH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, threads, smem));
+    if (blocks_per_sm < 1)
+    {
+      set_error("scatter_pair_kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+      return SMESH_ERR_UNSUPPORTED;
+    }
+    configured_smem = smem;
+    configured_threads = threads;
+    configured_device = device;
+  }
+  const int tile_px = cfg.consumer_warps * 64;
+  args.ntiles = (args.npix + tile_px - 1) / tile_px;
+  args.stages = cfg.stages;
+  int64_t blocks = (int64_t) num_sms() * blocks_per_sm;
+  if (blocks > args.ntiles) blocks = args.ntiles;
+  if (blocks < 1) return SMESH_OK;
+  kernel<<<(unsigned) blocks, threads, smem, stream>>>(args);
+  SMESH_LAUNCH_CHECK("scatter_pair_kernel");
+  return SMESH_OK;
+}
+
 template <int KIND>
 static int launch_scatter(const ScatterArgs& args, cudaStream_t stream)
 {
   RingConfig cfg;
   const bool aligned = (reinterpret_cast<uintptr_t>(args.probs) & 15) == 0;
+  static const bool no_pair = getenv("SMESH_NO_PAIR") != nullptr;
   if (aligned && ring_config(args.C, cfg))
   {
+    if (KIND != SMESH_KIND_SUMMAX && !no_pair && (reinterpret_cast<uintptr_t>(args.ids) & 7) == 0)
+    {
+      // narrow class vectors: two pixels per lane
+      switch (args.C)
+      {
+        case 19:
+        {
+          static const bool tma_flush = getenv("SMESH_TMA_FLUSH") ? atoi(getenv("SMESH_TMA_FLUSH")) != 0 : true;
+          constexpr int K = KIND == SMESH_KIND_SUMMAX ? SMESH_KIND_SUM : KIND;
+          return tma_flush ? launch_scatter_pair<K, 19, true>(args, stream) : launch_scatter_pair<K, 19, false>(args, stream);
+        }
+        default: break;
+      }
+    }
     switch (args.C)
     {
       case 19: return launch_scatter_ring<KIND, 19>(args, cfg, stream);
@@ -776,6 +1169,7 @@ static ScatterArgs make_scatter_args(const uint32_t* ids32, const float* probs, 
   args.stages = 0;
   args.count_mask = epoch != 0 ? COUNT_MASK : 0xFFFFFFFFu;
   args.run_cap = scatter_run_cap();
+  args.debug_skip = getenv("SMESH_DEBUG_SKIP") ? (uint32_t) atoi(getenv("SMESH_DEBUG_SKIP")) : 0u;
   args.iew = iew;
   return args;
 }
