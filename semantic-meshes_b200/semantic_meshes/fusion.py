@@ -228,9 +228,8 @@ class MeshAggregator:
         """Sum the raw accumulators of all ranks in place (one NCCL all-reduce of P x Cpad floats). Every aggregator
         kind accumulates by addition (mul adds -log p, +inf stays absorbing), so the sum of per-rank accumulators equals
         the accumulator of all views added on one GPU up to float reassociation."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self._acc, op=dist.ReduceOp.SUM, group=group)
+        from .distributed import allreduce_accumulator
+        allreduce_accumulator(self._acc, group=group)
 
     def state(self):
         """Raw accumulator (P, C) as a torch CUDA tensor (a view without the alignment padding)."""
