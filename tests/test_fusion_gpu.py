@@ -220,6 +220,34 @@ def test_error_behaviour(sm):
     sm.fusion.MeshAggregator(primitives=P, classes=C, aggregator="mul", images_equal_weight=0.25)
 
 
+@pytest.mark.parametrize("kind", ["sum", "mul"])
+@pytest.mark.parametrize("shape", [(40, 64), (9, 320), (33, 516), (64, 20), (31, 33)])
+def test_pair_kernel_shapes(sm, kind, shape):
+    """C = 19 takes the two-pixels-per-lane kernel: tiles that end inside a column, columns shorter than a tile, even and
+    odd pixel counts, weights, large faces with runs longer than a warp tile."""
+    import torch
+    W, H = shape
+    C, P = 19, 120
+    rng = np.random.default_rng(W * 1000 + H)
+    agg = sm.fusion.MeshAggregator(primitives=P, classes=C, aggregator=kind)
+    ref = oracle.Aggregator(P, C, kind)
+    for v in range(3):
+        ids, probs = make_view(rng, W, H, C, P, block=(1, 3, 7)[v])
+        wts = (rng.random((W, H)) * 2).astype(np.float32) if v == 2 else None
+        agg.add(torch.from_numpy(ids.view(np.int32)).cuda(), torch.from_numpy(probs).cuda(),
+                None if wts is None else torch.from_numpy(wts).cuda())
+        ref.add(ids, probs, wts)
+    assert_acc_close(kind, agg.state().cpu().numpy(), ref.acc)
+    # the transposed layout sweeps along the other image axis
+    agg2 = sm.fusion.MeshAggregator(primitives=P, classes=C, aggregator=kind)
+    ids, probs = make_view(rng, W, H, C, P, block=4)
+    ref2 = oracle.Aggregator(P, C, kind)
+    ref2.add(ids, probs)
+    pr_hw = torch.from_numpy(np.ascontiguousarray(probs.transpose(1, 0, 2))).cuda()
+    agg2.add(torch.from_numpy(ids.view(np.int32)).cuda(), pr_hw.permute(1, 0, 2))
+    assert_acc_close(kind, agg2.state().cpu().numpy(), ref2.acc)
+
+
 def test_count_epoch_wraparound(sm):
     """The per-view pixel counters are tagged with an 8-bit epoch instead of being cleared (include/smesh.h); 600 views
     cross the wrap twice, and the face -> pixel-count mapping changes every view."""

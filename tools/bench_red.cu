@@ -9,6 +9,10 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#ifndef STRIDE
+#define STRIDE 20
+#endif
+
 __device__ __forceinline__ void red_v4(float* p, float a, float b, float c, float d)
 {
   asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -23,7 +27,7 @@ __global__ void __launch_bounds__(256) k_mode0(float* acc, const uint32_t* rows,
 {
   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
   {
-    float* dst = acc + (size_t) rows[i] * 20;
+    float* dst = acc + (size_t) rows[i] * STRIDE;
 #pragma unroll
     for (int j = 0; j < 5; j++) red_v4(dst + 4 * j, 1.f, 2.f, 3.f, 4.f);
   }
@@ -37,7 +41,7 @@ __global__ void __launch_bounds__(256) k_mode1(float* acc, const uint32_t* rows,
   {
     const int64_t r = it / 5;
     const int j = (int) (it - r * 5);
-    red_v4(acc + (size_t) rows[r] * 20 + 4 * j, 1.f, 2.f, 3.f, 4.f);
+    red_v4(acc + (size_t) rows[r] * STRIDE + 4 * j, 1.f, 2.f, 3.f, 4.f);
   }
 }
 
@@ -48,20 +52,20 @@ __global__ void __launch_bounds__(256) k_mode3(float* acc, const uint32_t* rows,
   {
     const int64_t r = it / 20;
     const int j = (int) (it - r * 20);
-    red_f32(acc + (size_t) rows[r] * 20 + j, 1.f);
+    red_f32(acc + (size_t) rows[r] * STRIDE + j, 1.f);
   }
 }
 
 __global__ void __launch_bounds__(256) k_mode2(float* acc, const uint32_t* rows, int64_t n)
 {
-  __shared__ __align__(16) float stage[256 * 20];
-  float* mine = stage + threadIdx.x * 20;
+  __shared__ __align__(16) float stage[256 * STRIDE];
+  float* mine = stage + threadIdx.x * STRIDE;
   for (int j = 0; j < 20; j++) mine[j] = 1.f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
   {
-    float* dst = acc + (size_t) rows[i] * 20;
+    float* dst = acc + (size_t) rows[i] * STRIDE;
     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 80;" ::"l"(dst), "r"(smem_u32(mine)) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
@@ -73,7 +77,7 @@ int main(int argc, char** argv)
   const int64_t P = 2000000, n = 2 * 1024 * 1024;
   float* acc;
   uint32_t* rows;
-  cudaMalloc(&acc, P * 80);
+  cudaMalloc(&acc, P * STRIDE * 4);
   cudaMalloc(&rows, n * 4);
   uint32_t* h = (uint32_t*) malloc(n * 4);
   for (int window = 0; window < 2; window++)
@@ -84,7 +88,7 @@ int main(int argc, char** argv)
     cudaMemcpy(rows, h, n * 4, cudaMemcpyHostToDevice);
     for (int mode = 0; mode < 4; mode++)
     {
-      cudaMemset(acc, 0, P * 80);
+      cudaMemset(acc, 0, P * STRIDE * 4);
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0);
       cudaEventCreate(&e1);
@@ -105,7 +109,7 @@ int main(int argc, char** argv)
       }
       cudaError_t err = cudaGetLastError();
       float chk[20];
-      cudaMemcpy(chk, acc + (size_t) h[0] * 20, 80, cudaMemcpyDeviceToHost);
+      cudaMemcpy(chk, acc + (size_t) h[0] * STRIDE, 80, cudaMemcpyDeviceToHost);
       printf("range %8lld rows, mode %d: %8.1f us for %lld row updates (%.2f ns/row, %.1f Mrow/s) err=%s chk=%g %g\n", (long long) range,
              mode, best * 1e3, (long long) n, best * 1e6 / n, n / best / 1e3, cudaGetErrorString(err), chk[0], chk[19]);
     }

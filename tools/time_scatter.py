@@ -1,4 +1,4 @@
-"""GPU box: time the scatter kernel alone on one bench config (used with SMESH_SCATTER_NW / SMESH_SCATTER_STAGES)."""
+"""GPU box: time the scatter kernel alone on one bench config (used with the SMESH_* tuning variables)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "semantic-meshes_b200")]
@@ -8,6 +8,7 @@ from semantic_meshes import synthetic, _lib
 import bench
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 cfg = bench.CONFIGS[name]
 W, H, C = cfg["W"], cfg["H"], cfg["C"]
 mesh, cams = bench.build_scene(cfg, 0, B)
@@ -18,7 +19,7 @@ probs = [synthetic.predictions_torch(W, H, C, seed=b, device="cuda") for b in ra
 ids = [renderer.render(cams[b])[0] for b in range(B)]
 stream = torch.cuda.current_stream().cuda_stream
 ev = []
-for rep in range(6):
+for rep in range(reps + 1):
     agg.restart_epochs()
     for b in range(B):
         _lib.check(_lib.lib.smesh_fuse_count(ids[b].data_ptr(), _lib.ID_I32, H, 1, W, H, P, agg._counts.data_ptr(), b + 1, None, stream))
@@ -30,4 +31,5 @@ for rep in range(6):
             ev.append((e0, e1))
 torch.cuda.synchronize()
 t = np.array([a.elapsed_time(b) for a, b in ev]) * 1e3
-print(f"{name} NW={os.environ.get('SMESH_SCATTER_NW','-')} ST={os.environ.get('SMESH_SCATTER_STAGES','-')}: scatter {t.mean():.1f} us (min {t.min():.1f}, max {t.max():.1f}); input-only {(4*W*H*(C+1))/t.mean()/1e3:.0f} GB/s")
+tag = " ".join(f"{k[6:]}={v}" for k, v in sorted(os.environ.items()) if k.startswith("SMESH_"))
+print(f"{name} [{tag}]: scatter median {np.median(t):.1f} us (mean {t.mean():.1f}, min {t.min():.1f}, max {t.max():.1f}); input-only {(4*W*H*(C+1))/np.median(t)/1e3:.0f} GB/s")
