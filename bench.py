@@ -149,11 +149,17 @@ def run_ours(args, cfg):
         synthetic.predictions_torch(W, H, C, seed=1000 * rank + b, device=dev, out=probs[b])
     ids_all = torch.empty((B, W, H), dtype=torch.int32, device=dev)
 
+    from semantic_meshes.pipeline import ViewPipeline
+    pipe = ViewPipeline(renderer, agg)
+
     def step():
         agg.restart_epochs()  # the step is replayed as a graph: every replay must see the same count epochs (smesh.h)
-        for b in range(B):
-            idx, _ = renderer.render(cams[b])
-            agg.add(idx, probs[b])
+        if args.no_overlap:
+            for b in range(B):
+                idx, _ = renderer.render(cams[b])
+                agg.add(idx, probs[b])
+        else:
+            pipe.run(cams, probs)  # same work, render of view b+1 overlapped with the fusion of view b (two streams)
 
     # per-view statistics (outside any timed region): accepted pixels and touched faces
     accepted, touched, covered = [], [], []
@@ -303,7 +309,8 @@ def run_ours(args, cfg):
                    "classes": C, "aggregator": "sum", "images_equal_weight": 0.5, "parallelism": f"view-shard x{world}",
                    "pixels_covered": float(np.mean(covered)), "faces_touched_per_view": float(np.mean(touched)),
                    "cache": f"{B} distinct views of {bytes_inputs / 1e6:.0f} MB cycled per step (>> 126 MB L2)",
-                   "cuda_graph": graph is not None, "allreduce_in_timed_region": world > 1},
+                   "cuda_graph": graph is not None, "allreduce_in_timed_region": world > 1,
+                   "render_add_overlap": not args.no_overlap},
         "mpixel_face_scatters_per_s": value * float(np.mean(accepted)) / 1e6,
         "stages": {"render_ms_per_view": render_ms, "add_ms_per_view": add_ms, "scatter_kernel_ms": scatter_ms,
                    "render_views_per_s": 1e3 / render_ms, "add_views_per_s": 1e3 / add_ms, "allreduce_ms": allreduce_ms},
@@ -430,6 +437,7 @@ def main():
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true", help="render and add strictly one after the other on one stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-views", type=int, default=3)
     args = ap.parse_args()

@@ -8,5 +8,6 @@ Device buffers are torch tensors; the arithmetic runs in hand-written sm_100a CU
 from . import data
 from . import fusion
 from . import render
+from . import pipeline
 
-__all__ = ["data", "fusion", "render"]
+__all__ = ["data", "fusion", "render", "pipeline"]

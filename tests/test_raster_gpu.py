@@ -126,6 +126,36 @@ def test_offscreen_drop_is_exact(sm):
         assert (gi != BG).mean() > 0.3
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_triangle_soups(sm, seed):
+    """Random soups of visible triangles of all sizes (sub-pixel to 60 px), orientations (edge-on included), shapes (20 %
+    slivers) and depths, several cameras: index and depth bit-exact against the oracle."""
+    from semantic_meshes import synthetic
+    from semantic_meshes.data import Camera, Ply
+    rng = np.random.default_rng(1000 + seed)
+    W, H, f = 257, 131, 210.0
+    n = 5000
+    z = rng.uniform(0.3, 8.0, (n, 1))
+    cx = rng.uniform(-10, W + 10, (n, 1))
+    cy = rng.uniform(-10, H + 10, (n, 1))
+    centre = np.concatenate([(cx - W / 2) * z / f, (cy - H / 2) * z / f, z], axis=1)
+    size_px = rng.choice([0.3, 1.0, 3.0, 8.0, 25.0, 60.0], (n, 1, 1), p=[0.1, 0.2, 0.3, 0.2, 0.15, 0.05])
+    offs = rng.normal(size=(n, 3, 3)) * size_px * z[:, :, None] / f * 0.5
+    flat = rng.random(n) < 0.5
+    offs[flat, :, 2] *= 0.05                                     # mostly fronto-parallel, the rest arbitrary tilt
+    sliver = rng.random(n) < 0.2
+    offs[sliver, 2] = offs[sliver, 1] * (1 + 0.05 * rng.normal(size=(sliver.sum(), 1)))
+    verts = (centre[:, None, :] + offs).reshape(-1, 3).astype(np.float32)
+    mesh = Ply.from_arrays(verts, np.arange(3 * n, dtype=np.int32).reshape(n, 3))
+    renderer = sm.render.triangles(mesh)
+    for k in range(3):
+        R, t = synthetic.look_at(np.array([0.1 * k, -0.07 * k, -0.2 * k]), np.array([0.05 * k, 0.0, 4.0]), up=(0, -1, 0))
+        cam = Camera(R, t, np.array([W, H]), np.array([f, f * 1.02]), np.array([W / 2 + 0.3, H / 2 - 0.4]))
+        gi, gd, oi, od = render_both(sm, mesh, cam, renderer)
+        assert_bit_exact(gi, gd, oi, od)
+        assert (gi != BG).mean() > 0.5
+
+
 def test_intrinsics_change_rebuilds_ray_table(sm):
     """The per-pixel ray normalisation is cached per intrinsics inside the renderer's workspace."""
     from semantic_meshes import synthetic
@@ -170,6 +200,32 @@ def test_render_then_add_pipeline(sm):
         agg.add(idx, pred)
         ref.add(idx.cpu().numpy().view(np.uint32), pred.cpu().numpy())
     np.testing.assert_allclose(agg.get(), ref.get(), rtol=1e-5, atol=1e-7)
+
+
+def test_overlapped_pipeline_matches_sequential(sm):
+    """pipeline.ViewPipeline (render of view v+1 on a second stream while view v is fused) == the sequential loop."""
+    import torch
+    from semantic_meshes import synthetic
+    from semantic_meshes.pipeline import ViewPipeline
+    W, H, C = 160, 128, 19
+    mesh = synthetic.mesh("terrain", 6000, seed=4)
+    renderer = sm.render.triangles(mesh)
+    P = renderer.getPrimitivesNum()
+    cams = synthetic.terrain_cameras(6, W, H, 6000, tris_per_view=2500, seed=9)
+    preds = torch.stack([synthetic.predictions_torch(W, H, C, seed=v, device="cuda") for v in range(len(cams))])
+    seq, ovl = sm.fusion.MeshAggregator(P, C), sm.fusion.MeshAggregator(P, C)
+    ids_seq = []
+    for v, cam in enumerate(cams):
+        idx, _ = renderer.render(cam)
+        seq.add(idx, preds[v])
+        ids_seq.append(idx.clone())
+    for rep in range(3):  # repeated: stream hand-over between runs
+        kept = ViewPipeline(renderer, ovl).run(cams, preds, keep_indices=True) if rep == 0 else pipe.run(cams, preds, keep_indices=True)
+        pipe = ViewPipeline(renderer, ovl) if rep == 0 else pipe
+        torch.cuda.synchronize()
+        for a, b in zip(kept, ids_seq):
+            assert torch.equal(a, b)
+    torch.testing.assert_close(ovl.state(), 3 * seq.state(), rtol=1e-5, atol=1e-6)
 
 
 @pytest.mark.skipif(not os.path.exists(oracle.ref_raster_path()), reason="genuine reference kernel build absent")
