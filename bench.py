@@ -199,6 +199,9 @@ def run_ours(args, cfg):
     if dist is not None:
         dist.barrier()
         torch.cuda.synchronize()
+    profile_range = os.environ.get("SMESH_PROFILE_RANGE") == "1"  # ncu --profile-from-start off: timed region only
+    if profile_range:
+        torch.cuda.cudart().cudaProfilerStart()
     t0 = time.perf_counter()
     start.record()
     for _ in range(args.steps):
@@ -207,6 +210,8 @@ def run_ours(args, cfg):
     agg.allreduce()
     stop.record()
     torch.cuda.synchronize()
+    if profile_range:
+        torch.cuda.cudart().cudaProfilerStop()
     if dist is not None:
         dist.barrier()
         torch.cuda.synchronize()
