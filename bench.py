@@ -301,9 +301,9 @@ def run_ours(args, cfg):
         e2e_ms = float(t[0])
     e2e_value = e2e_steps * B * world / (e2e_ms * 1e-3)
 
-    # kernel launches of ours inside the timed region: per view 5 (render: setup, cull, bin, big, resolve) + 2 (add: count,
-    # scatter)
-    gpu_launches = args.steps * B * 7
+    # kernel launches of ours inside the timed region: per view 4 (render: begin/cull, clusters, big, resolve) + 2 (add:
+    # count, scatter)
+    gpu_launches = args.steps * B * 6
 
     line = {
         "metric": "views/s (render + MeshAggregator.add per view), whole job",

@@ -64,35 +64,41 @@ const char* smesh_version(void);
  * Triangle::{precompute,intersect,rasterize} (tt/geometry/render/primitives/Triangle.h:47-164).
  * ------------------------------------------------------------------------------------------------------------- */
 
+/*
+ * Prepared mesh. smesh_raster_mesh_build turns the arrays TriangleRenderer's ctor uploads (TriangleRenderer.h:30-39) into
+ * one device blob, once per mesh: vertices repacked as float4, faces sorted along a Morton curve of their centroids and
+ * cut into clusters of 128 with a bounding sphere each (a view skips the clusters that are provably behind the camera or
+ * far outside the image), every face tagged "well shaped" (sine of the smallest angle >= 0.1) or not. The index image
+ * still reports ORIGINAL face indices. Results do not depend on the order of the faces.
+ *   verts   float32[V][3], faces int32[F][3] with 0 <= index < V   (F < 2^32 - 1, V < 2^31)
+ *   mesh_out / temp   256-byte aligned device buffers of the sizes smesh_raster_mesh_bytes reports; temp is scratch for
+ *           the build only (sort keys), mesh_out is what smesh_raster_render takes
+ */
+int smesh_raster_mesh_bytes(int64_t V, int64_t F, size_t* mesh_bytes_host, size_t* temp_bytes_host);
+int smesh_raster_mesh_build(const float* verts, int64_t V, const int32_t* faces, int64_t F, void* mesh_out, size_t mesh_bytes,
+                            void* temp, size_t temp_bytes, void* stream);
+
 /* Bytes of device scratch smesh_raster_render needs for a mesh of V vertices / F triangles at resolution W x H
- * (camera-space vertex cache, per-view ray tables, packed 64-bit depth|index buffer, large-triangle queue). */
+ * (per-view ray tables, packed 64-bit depth|index buffer, cluster and large-triangle queues). */
 int smesh_raster_workspace_bytes(int64_t V, int64_t F, int W, int H, size_t* bytes_host);
-
-/* Optional per-face mesh property (1 byte per face) that lets the rasterizer drop triangles far outside the image
- * without testing them (results stay identical, see smesh_raster.cu far_offscreen()). */
-#define SMESH_FACE_WELL_SHAPED 1 /* sine of the smallest angle >= 0.1 */
-
-/* flags_out uint8[F] = SMESH_FACE_WELL_SHAPED or 0 per face; view independent, compute once per mesh. */
-int smesh_raster_face_flags(const float* verts, int64_t V, const int32_t* faces, int64_t F, uint8_t* flags_out,
-                            void* stream);
 
 /*
  * Render one view: per pixel the index of the nearest hit triangle and its camera-space depth z.
- *   verts   float32[V][3], faces int32[F][3]      (what TriangleRenderer's ctor uploads, TriangleRenderer.h:30-39)
- *   face_flags uint8[F] from smesh_raster_face_flags, or NULL (every triangle takes the exact per-pixel path)
+ *   mesh    the blob smesh_raster_mesh_build filled for (V, F)
  *   R_host  float[9] row-major rotation, t_host float[3]   (Camera::extr, include/semantic_meshes/render/Camera.h:12)
  *   f_host  double[2] focal lengths, c_host double[2] principal point (Camera::intr; the Python Camera rounds its
  *           inputs to float first and then widens, python/semantic_meshes/include/Camera.h:19-54 - the caller does it)
  *   W, H    Camera::resolution (1 <= W, H <= 65536)
  *   workspace  device scratch of smesh_raster_workspace_bytes(V, F, W, H) bytes; ZERO-FILL it once after allocating it
- *           (it caches a per-pixel table keyed by the intrinsics) and keep it for the next views of the same mesh
+ *           (it caches a per-pixel table keyed by the intrinsics and the cleared depth buffer) and keep it for the next
+ *           views of the same mesh; one workspace serves one stream at a time
  *   idx_out uint32[W][H] (0xFFFFFFFF where nothing is hit), depth_out float32[W][H] (+inf where nothing is hit)
  * Results are bit-identical to the reference kernel as compiled by nvcc 12.9 for sm_100a, with the one documented
  * strengthening that exact depth ties go to the lowest triangle index (the reference is order-dependent there).
  */
-int smesh_raster_render(const float* verts, int64_t V, const int32_t* faces, int64_t F, const uint8_t* face_flags,
-                        const float* R_host, const float* t_host, const double* f_host, const double* c_host, int W, int H,
-                        void* workspace, size_t workspace_bytes, uint32_t* idx_out, float* depth_out, void* stream);
+int smesh_raster_render(const void* mesh, size_t mesh_bytes, int64_t V, int64_t F, const float* R_host, const float* t_host,
+                        const double* f_host, const double* c_host, int W, int H, void* workspace, size_t workspace_bytes,
+                        uint32_t* idx_out, float* depth_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Label fusion: replaces ModelAggregator::{add1,add2,get,reset} (python/semantic_meshes/include/Fusion.h:42-76) ->

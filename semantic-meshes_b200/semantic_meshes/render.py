@@ -28,20 +28,36 @@ class TriangleRenderer:
         if faces.size and (faces.min() < 0 or faces.max() >= verts.shape[0]):
             raise ValueError("render.triangles: face index out of range")
         self._V, self._F = int(verts.shape[0]), int(faces.shape[0])
-        # what TriangleRenderer's ctor uploads (TriangleRenderer.h:30-39)
-        self._verts = torch.from_numpy(verts).to(self.device)
-        self._faces = torch.from_numpy(faces).to(self.device)
-        # per-face "well shaped" flags: lets the kernel skip triangles far outside the image (include/smesh.h)
-        self._face_flags = torch.zeros((max(self._F, 1),), dtype=torch.uint8, device=self.device)
+        # what TriangleRenderer's ctor uploads (TriangleRenderer.h:30-39), turned into the prepared mesh once: float4
+        # vertices, Morton-sorted faces in clusters of 128 with bounding spheres (include/smesh.h)
+        mesh_bytes, temp_bytes = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        _lib.check(_lib.lib.smesh_raster_mesh_bytes(self._V, self._F, ctypes.byref(mesh_bytes), ctypes.byref(temp_bytes)))
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib.smesh_raster_face_flags(self._verts.data_ptr(), self._V, self._faces.data_ptr(), self._F,
-                                                        self._face_flags.data_ptr(),
-                                                        torch.cuda.current_stream().cuda_stream))
+            verts_d = torch.from_numpy(verts).to(self.device)
+            faces_d = torch.from_numpy(faces).to(self.device)
+            self._mesh = torch.zeros(mesh_bytes.value, dtype=torch.uint8, device=self.device)
+            temp = torch.empty(temp_bytes.value, dtype=torch.uint8, device=self.device)
+            _lib.check(_lib.lib.smesh_raster_mesh_build(verts_d.data_ptr(), self._V, faces_d.data_ptr(), self._F,
+                                                        self._mesh.data_ptr(), self._mesh.numel(), temp.data_ptr(),
+                                                        temp.numel(), torch.cuda.current_stream().cuda_stream))
+            torch.cuda.current_stream().synchronize()  # temp / verts_d / faces_d are released on return
         self._workspace = None
         self._workspace_res = None
 
     def getPrimitivesNum(self):
         return self._F
+
+    def face_flags(self):
+        """Diagnostics: uint8 numpy (F,), 1 where the prepared mesh tagged the face "well shaped" (include/smesh.h)."""
+        import numpy as np
+        V, F = self._V, self._F
+        nc = (F + 127) // 128
+        off = ((max(V, 1) * 16 + 255) // 256) * 256
+        rec = self._mesh[off:off + nc * 128 * 16].view(self._torch.int32).view(-1, 4).cpu().numpy()
+        rec = rec[rec[:, 3] != -1]
+        out = np.zeros(F, dtype=np.uint8)
+        out[rec[:, 3].astype(np.int64)] = (rec[:, 0] < 0).astype(np.uint8)
+        return out
 
     def _ensure_workspace(self, W, H):
         if self._workspace_res != (W, H):
@@ -71,10 +87,9 @@ class TriangleRenderer:
             depth = torch.empty((W, H), dtype=torch.float32, device=self.device)
             R, t = camera.rotation, camera.translation
             f, c = camera.focal_lengths, camera.principal_point
-            rc = _lib.lib.smesh_raster_render(self._verts.data_ptr(), self._V, self._faces.data_ptr(), self._F,
-                                              self._face_flags.data_ptr(), R.ctypes.data, t.ctypes.data, f.ctypes.data, c.ctypes.data, W, H,
-                                              ws.data_ptr(), ws.numel(), idx.data_ptr(), depth.data_ptr(),
-                                              torch.cuda.current_stream().cuda_stream)
+            rc = _lib.lib.smesh_raster_render(self._mesh.data_ptr(), self._mesh.numel(), self._V, self._F, R.ctypes.data,
+                                              t.ctypes.data, f.ctypes.data, c.ctypes.data, W, H, ws.data_ptr(), ws.numel(),
+                                              idx.data_ptr(), depth.data_ptr(), torch.cuda.current_stream().cuda_stream)
         _lib.check(rc)
         if capsule:
             from torch.utils.dlpack import to_dlpack

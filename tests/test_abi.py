@@ -33,7 +33,7 @@ def test_workspace_bytes_and_errors():
     from semantic_meshes import _lib
     n = ctypes.c_size_t(0)
     assert _lib.lib.smesh_raster_workspace_bytes(642, 1280, 256, 256, ctypes.byref(n)) == 0
-    assert n.value >= 642 * 16 + 256 * 256 * 12 + 1280 * 4
+    assert n.value >= 256 * 256 * 12 + 1280 * 8
     assert _lib.lib.smesh_raster_workspace_bytes(10, 10, 0, 5, ctypes.byref(n)) == _lib.ERR_INVALID_ARGUMENT
     assert b"invalid argument" in _lib.lib.smesh_last_error()
     with pytest.raises(ValueError):
@@ -42,8 +42,13 @@ def test_workspace_bytes_and_errors():
     assert _lib.lib.smesh_fuse_add(7, None, 0, 0, 0, None, None, 0, 0, 4, 4, 3, 10, 0.5, None, 1, None, None, None) \
         == _lib.ERR_INVALID_ARGUMENT
     assert _lib.lib.smesh_fuse_get(0, None, 5, 0, None, None) == _lib.ERR_INVALID_ARGUMENT
-    assert _lib.lib.smesh_raster_render(None, 0, None, 0, None, None, None, None, None, 4, 4, None, 0, None, None, None) \
+    assert _lib.lib.smesh_raster_render(None, 0, 0, 0, None, None, None, None, 4, 4, None, 0, None, None, None) \
         == _lib.ERR_INVALID_ARGUMENT
+    m, t = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    assert _lib.lib.smesh_raster_mesh_bytes(642, 1280, ctypes.byref(m), ctypes.byref(t)) == 0
+    assert m.value >= 642 * 16 + 1280 * 16 + 10 * 16 and t.value >= 1280 * 24
+    assert _lib.lib.smesh_raster_mesh_bytes(-1, 5, ctypes.byref(m), ctypes.byref(t)) == _lib.ERR_INVALID_ARGUMENT
+    assert _lib.lib.smesh_raster_mesh_build(None, 3, None, 1, None, 0, None, 0, None) == _lib.ERR_INVALID_ARGUMENT
 
 
 def test_no_cpu_fallback():
