@@ -1123,7 +1123,8 @@ static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
   const int tile_px = cfg.consumer_warps * 64;
   args.ntiles = (args.npix + tile_px - 1) / tile_px;
   args.stages = cfg.stages;
-  int64_t blocks = (int64_t) num_sms() * blocks_per_sm;
+  static const int env_ctas = getenv("SMESH_PAIR_CTAS") ? atoi(getenv("SMESH_PAIR_CTAS")) : 0; // tuning
+  int64_t blocks = (int64_t) num_sms() * (env_ctas >= 1 && env_ctas < blocks_per_sm ? env_ctas : blocks_per_sm);
   if (blocks > args.ntiles) blocks = args.ntiles;
   if (blocks < 1) return SMESH_OK;
   kernel<<<(unsigned) blocks, threads, smem, stream>>>(args);

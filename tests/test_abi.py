@@ -33,7 +33,7 @@ def test_workspace_bytes_and_errors():
     from semantic_meshes import _lib
     n = ctypes.c_size_t(0)
     assert _lib.lib.smesh_raster_workspace_bytes(642, 1280, 256, 256, ctypes.byref(n)) == 0
-    assert n.value >= 256 * 256 * 12 + 1280 * 8
+    assert n.value >= 256 * 256 * 8 + 1280 * 8
     assert _lib.lib.smesh_raster_workspace_bytes(10, 10, 0, 5, ctypes.byref(n)) == _lib.ERR_INVALID_ARGUMENT
     assert b"invalid argument" in _lib.lib.smesh_last_error()
     with pytest.raises(ValueError):

@@ -38,4 +38,13 @@ for b in blocks:
     print(b["name"][:150]); print(f"total warp instr {tot}, samples {tots}")
     for (ln, src), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
         print(f"{ln:5d} {100*v[0]/max(tot,1):5.1f}% inst  {100*v[2]/max(tots,1):5.1f}% stall  thr/inst {v[1]/max(v[0],1):4.1f}  {src[:90]}")
+    # optional region summary: extra args "name:lo-hi"
+    regs = [a for a in sys.argv[4:] if ":" in a]
+    if regs:
+        print("regions:")
+        for r in regs:
+            name, rng = r.split(":"); lo, hi = (int(v) for v in rng.split("-"))
+            vi = sum(v[0] for (ln, _), v in agg.items() if lo <= ln <= hi); vs = sum(v[2] for (ln, _), v in agg.items() if lo <= ln <= hi)
+            vt = sum(v[1] for (ln, _), v in agg.items() if lo <= ln <= hi)
+            print(f"  {name:18s} {100*vi/max(tot,1):5.1f}% inst ({vi/1e6:6.2f}M) {100*vs/max(tots,1):5.1f}% stall  thr/inst {vt/max(vi,1):4.1f}")
     break
