@@ -242,6 +242,31 @@ def test_many_clusters_are_culled_exactly(sm):
         assert_bit_exact(gi, gd, oi, od)
 
 
+@pytest.mark.parametrize("tilt_deg", [35.0, 50.0, 65.0, 85.0])
+def test_camera_plane_straddlers(sm, tilt_deg):
+    """A camera high above a large terrain, tilted: the camera plane z = 0 cuts the terrain, hundreds of triangles have
+    corners on both sides of it and get whole-image bounding boxes from meaningless projections. The reference tests all
+    those pixels; here most such triangles are dropped by far_offscreen() (conditions (a)-(d)), the rest (at 85 degrees the
+    horizon is in the image) take the exact path. Either way the image must equal the oracle's."""
+    from semantic_meshes import synthetic
+    from semantic_meshes.data import Camera
+    F = 120_000
+    mesh = synthetic.mesh("terrain", F, seed=21)
+    renderer = sm.render.triangles(mesh)
+    L = np.sqrt(F / 2.0)
+    W, H = (128, 96) if tilt_deg < 80 else (64, 48)
+    tilt = np.radians(tilt_deg)
+    for k, yaw in enumerate((0.3, 2.1, 4.0)):
+        target = np.array([L * (0.35 + 0.1 * k), L * (0.5 - 0.07 * k), 0.0])
+        d = np.array([np.sin(tilt) * np.cos(yaw), np.sin(tilt) * np.sin(yaw), np.cos(tilt)])
+        eye = target + d * 25.0
+        R, t = synthetic.look_at(eye, target, up=(np.cos(yaw + 1.0), np.sin(yaw + 1.0), 0.0))
+        cam = Camera(R, t, np.array([W, H]), np.array([0.9 * W, 0.9 * W]), np.array([W / 2, H / 2]))
+        gi, gd, oi, od = render_both(sm, mesh, cam, renderer)
+        assert_bit_exact(gi, gd, oi, od)
+        assert (gi != BG).mean() > 0.3
+
+
 def test_intrinsics_change_rebuilds_ray_table(sm):
     """The per-pixel ray normalisation is cached per intrinsics inside the renderer's workspace."""
     from semantic_meshes import synthetic
