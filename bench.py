@@ -234,17 +234,35 @@ def run_ours(args, cfg):
     reps = max(1, min(args.steps, 20))
 
     def timed(fn, n):
+        """Mean device time of fn(): captured once into a CUDA graph and replayed n times (eager launches from Python
+        would measure the host, not the kernels); falls back to eager launches if capture fails."""
+        fn()
+        torch.cuda.synchronize()
+        run = fn
+        if use_graph:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                run = g.replay
+            except Exception:
+                torch.cuda.synchronize()
+        run()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         torch.cuda.synchronize()
         e0.record()
         for _ in range(n):
-            fn()
+            run()
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
 
+    def add_all():
+        agg.restart_epochs()
+        agg.add_batch(ids_all, probs)
+
     render_ms = timed(lambda: [renderer.render(cams[b]) for b in range(B)], reps) / B
-    add_ms = timed(lambda: agg.add_batch(ids_all, probs), reps) / B
+    add_ms = timed(add_all, reps) / B
     scatter_events = []
     torch.cuda.synchronize()
     for _ in range(reps):
