@@ -248,6 +248,49 @@ def test_pair_kernel_shapes(sm, kind, shape):
     assert_acc_close(kind, agg2.state().cpu().numpy(), ref2.acc)
 
 
+@pytest.mark.parametrize("kind", ["sum", "mul"])
+@pytest.mark.parametrize("shape", [(40, 64), (23, 128), (50, 260), (17, 1080), (300, 256), (7, 2048), (64, 516)])
+def test_tall_column_shapes(sm, kind, shape):
+    """C = 19 images with tall columns (64 ... 2048 pixels, not always a multiple of the 256-pixel tile): faces from 1 pixel
+    to wider than the image, faces that reappear in every third column, weights, and a face change at every pixel
+    (block = 1: as many run sums per warp tile as there are pixels)."""
+    import torch
+    W, H = shape
+    C, P = 19, 400
+    rng = np.random.default_rng(W * 977 + H)
+    agg = sm.fusion.MeshAggregator(primitives=P, classes=C, aggregator=kind)
+    ref = oracle.Aggregator(P, C, kind)
+    for v, block in enumerate((1, 2, 5, 16, 64)):
+        ids, probs = make_view(rng, W, H, C, P, block=block, bg=0.05 if block > 1 else 0.3)
+        if block == 5:
+            ids[::3] = ids[0]                       # the same faces in every third column: a gap, then again
+        wts = (rng.random((W, H)) * 2).astype(np.float32) if v % 2 else None
+        agg.add(torch.from_numpy(ids.view(np.int32)).cuda(), torch.from_numpy(probs).cuda(),
+                None if wts is None else torch.from_numpy(wts).cuda())
+        ref.add(ids, probs, wts)
+    assert_acc_close(kind, agg.state().cpu().numpy(), ref.acc)
+    assert_get_close(kind, agg.get(), ref.get())
+
+
+def test_add_on_rendered_ids(sm):
+    """MeshAggregator.add on real index images (coherent faces of a dozen pixels, occlusion edges) at a size of several
+    hundred tiles per CTA, against the oracle."""
+    import torch
+    from semantic_meshes import synthetic
+    W, H, C = 640, 512, 19
+    mesh = synthetic.mesh("terrain", 60000, seed=5)
+    renderer = sm.render.triangles(mesh)
+    P = renderer.getPrimitivesNum()
+    agg = sm.fusion.MeshAggregator(primitives=P, classes=C)
+    ref = oracle.Aggregator(P, C)
+    for v, cam in enumerate(synthetic.terrain_cameras(3, W, H, 60000, tris_per_view=25000, seed=12)):
+        idx, _ = renderer.render(cam)
+        pred = synthetic.predictions_torch(W, H, C, seed=50 + v, device="cuda")
+        agg.add(idx, pred)
+        ref.add(idx.cpu().numpy().view(np.uint32), pred.cpu().numpy())
+    assert_acc_close("sum", agg.state().cpu().numpy(), ref.acc)
+
+
 def test_count_epoch_wraparound(sm):
     """The per-view pixel counters are tagged with an 8-bit epoch instead of being cleared (include/smesh.h); 600 views
     cross the wrap twice, and the face -> pixel-count mapping changes every view."""
