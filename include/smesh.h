@@ -100,6 +100,17 @@ int smesh_raster_render(const void* mesh, size_t mesh_bytes, int64_t V, int64_t 
                         const double* f_host, const double* c_host, int W, int H, void* workspace, size_t workspace_bytes,
                         uint32_t* idx_out, float* depth_out, void* stream);
 
+/*
+ * smesh_raster_render that also leaves the per-face pixel counts of the view (Mesh.h:90-93) in `counts` (uint32[F], the
+ * tagged counters described under "Label fusion" below) with epoch count_epoch in 1..255: the first half of
+ * ModelAggregator::add for an aggregator over the faces of this mesh, fused into the pass that writes the index image.
+ * Follow with smesh_fuse_scatter(ids32 = idx_out, same counts, same count_epoch).
+ */
+int smesh_raster_render_counted(const void* mesh, size_t mesh_bytes, int64_t V, int64_t F, const float* R_host,
+                                const float* t_host, const double* f_host, const double* c_host, int W, int H, void* workspace,
+                                size_t workspace_bytes, uint32_t* idx_out, float* depth_out, uint32_t* counts,
+                                uint32_t count_epoch, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Label fusion: replaces ModelAggregator::{add1,add2,get,reset} (python/semantic_meshes/include/Fusion.h:42-76) ->
  * semantic_meshes::ModelAggregator::{add,get,reset} (include/semantic_meshes/fusion/Mesh.h:57-133) with the chains

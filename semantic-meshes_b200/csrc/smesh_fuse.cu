@@ -13,7 +13,9 @@
 //                       sum, Mesh.h:98) and weight (Mesh.h:100-103), then lanes regroup as (run of equal face id, 4-class
 //                       chunk) to reduce the run in registers and issue ONE 128-bit red.global.add.v4.f32 per chunk into
 //                       the 16-byte padded accumulator row
-//   3. clear_kernel   - zero the touched counters again (cheaper than a P-sized memset per view)
+//                       (C = 19: scatter_pair_kernel, two pixels per lane; wide C: scatter_rows_kernel, lanes across the
+//                       classes of a pixel, rows read straight from global memory)
+//   3. clear_kernel   - only in the untagged-counter mode (images of >= 2^24 pixels): zero the touched counters again
 // No tensor cores: this is an irregular gather/scatter, not a contraction.
 #include "smesh_common.cuh"
 
@@ -902,6 +904,278 @@ __global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 2c. scatter, WIDE class vectors (C >= 32): lanes across the classes of one pixel.
+//
+// A warp takes 32 consecutive pixels: lane = pixel for the side inputs (id, per-face count, weight); then the lanes turn
+// across the class vector: a sub-group of LG = 8 / 16 / 32 lanes reads a pixel's row straight from global memory with
+// 128- or 64-bit loads (consecutive lanes, consecutive classes: fully coalesced, streaming, no shared memory), weights it
+// and keeps the sum of the current run of equal face ids in registers, walking its share of the 32 pixels in order; a run
+// ends with one vector reduction per lane into the accumulator row (again consecutive lanes, consecutive addresses).
+// No shuffle scans, no staging, no divergence inside a sub-group.
+// The gate (Mesh.h:98) needs the SEQUENTIAL float sum of the row. The lanes form the sum in tree order; for
+// non-negative values the two orders differ by at most 2 C 2^-24 of the sum, so unless the tree sum is within 1e-3
+// (relative) of 0.5 - or a value is negative or NaN - the comparison `> 0.5` has the same outcome; otherwise one lane
+// recomputes the sum in the reference's order.
+// ---------------------------------------------------------------------------------------------------------------------
+
+template <int VW>
+__device__ __forceinline__ void row_load(const float* p, float (&v)[VW])
+{
+  if (VW == 4)
+  {
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1 % VW] = t.y; v[2 % VW] = t.z; v[3 % VW] = t.w;
+  }
+  else if (VW == 2)
+  {
+    const float2 t = __ldcs(reinterpret_cast<const float2*>(p));
+    v[0] = t.x; v[1 % VW] = t.y;
+  }
+  else
+  {
+    v[0] = __ldcs(p);
+  }
+}
+
+template <int VW>
+__device__ __forceinline__ void row_red(float* p, const float (&v)[VW])
+{
+  if (VW == 4)
+  {
+    red_add_v4(p, v[0], v[1 % VW], v[2 % VW], v[3 % VW]);
+  }
+  else if (VW == 2)
+  {
+    asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1 % VW]) : "memory");
+  }
+  else
+  {
+    red_add_f32(p, v[0]);
+  }
+}
+
+// VW = floats per lane and chunk (C % VW == 0), LG = lanes of a sub-group, NP = chunks per lane (ceil(C / VW / LG))
+template <int KIND, int VW, int LG, int NP>
+__global__ void __launch_bounds__(256) scatter_rows_kernel(ScatterArgs a)
+{
+  constexpr int U = NP <= 2 ? 4 : 2; // pixels whose rows are loaded before the first is reduced
+  constexpr int G = 32 / LG;         // sub-groups
+  constexpr int Rg = 32 / G;         // pixels of a sub-group per warp block
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LG, j = lane % LG;
+  const int K = a.C / VW;                        // chunks per row
+  const uint32_t P32 = (uint32_t) a.P;
+  const int64_t warp_global = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+
+  auto load_side = [&](int64_t base, uint32_t& id, float& wt) {
+    const int64_t i = base + lane;
+    id = INVALID_ID;
+    wt = 1.0f;
+    if (i < a.npix)
+    {
+      id = __ldg(a.ids + i);
+      if (a.weights != nullptr)
+      {
+        wt = __ldg(a.weights + i);
+      }
+    }
+    if (!(id < P32))
+    {
+      id = INVALID_ID;
+    }
+  };
+
+  int64_t base = warp_global * 32;
+  uint32_t id_next;
+  float wt_next;
+  load_side(base, id_next, wt_next);
+  for (; base < a.npix; base += nwarps * 32)
+  {
+    const uint32_t id = id_next;
+    const float wt = wt_next;
+    const uint32_t n = id != INVALID_ID ? __ldg(a.counts + id) : 1u;
+    load_side(base + nwarps * 32, id_next, wt_next); // the next block's ids are in flight while this one is reduced
+    const float w = pixel_weight(a.iew, n & a.count_mask, wt);
+
+    uint32_t cur = INVALID_ID;
+    float acc[NP][VW];
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+    {
+#pragma unroll
+      for (int k = 0; k < VW; k++)
+      {
+        acc[p][k] = 0.0f;
+      }
+    }
+    auto flush = [&]() {
+      if (cur != INVALID_ID)
+      {
+        float* dst = a.acc + (size_t) cur * a.Cpad;
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+        {
+          const int c = j + p * LG;
+          if (c < K)
+          {
+            row_red<VW>(dst + c * VW, acc[p]);
+          }
+#pragma unroll
+          for (int k = 0; k < VW; k++)
+          {
+            acc[p][k] = 0.0f;
+          }
+        }
+      }
+    };
+
+    // this lane's first chunk of the sub-group's first pixel (Rg and U divide evenly: no pixel is out of range)
+    const float* lane_row = a.probs + (size_t) base * a.C + (g * Rg) * a.C + j * VW;
+    static_assert(Rg % U == 0, "sub-group pixels come in whole batches");
+    for (int it = 0; it < Rg; it += U)
+    {
+      uint32_t idu[U];
+      float wu[U];
+      float v[U][NP][VW];
+#pragma unroll
+      for (int u = 0; u < U; u++)
+      {
+        const int q = g * Rg + it + u;           // pixel of the warp block this sub-group looks at
+        idu[u] = __shfl_sync(0xFFFFFFFFu, id, q);
+        wu[u] = __shfl_sync(0xFFFFFFFFu, w, q);
+        const float* row = lane_row + (it + u) * a.C;
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+        {
+#pragma unroll
+          for (int k = 0; k < VW; k++)
+          {
+            v[u][p][k] = 0.0f;
+          }
+          if (idu[u] != INVALID_ID && j + p * LG < K)
+          {
+            row_load<VW>(row + p * (LG * VW), v[u][p]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+      {
+        // ---- gate (Mesh.h:95-98) ----
+        float s = 0.0f;
+        uint32_t signs = 0u; // a negative value: the tree sum says nothing about the sequential one (a NaN shows in s)
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+        {
+#pragma unroll
+          for (int k = 0; k < VW; k++)
+          {
+            s += v[u][p][k];
+            signs |= __float_as_uint(v[u][p][k]);
+          }
+        }
+#pragma unroll
+        for (int o = LG >> 1; o > 0; o >>= 1)
+        {
+          s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        }
+        const uint32_t oddmask = __ballot_sync(0xFFFFFFFFu, (signs & 0x80000000u) != 0u);
+        const uint32_t gmask = (LG == 32 ? 0xFFFFFFFFu : ((1u << (LG % 32)) - 1u)) << (g * LG);
+        const bool unsure = (oddmask & gmask) != 0u || !(fabsf(s - 0.5f) > 1e-3f * fmaxf(s, 0.5f));
+        if (idu[u] != INVALID_ID && unsure)
+        {
+          // the reference's order, by the first lane of the sub-group (rare: a sum at the threshold, or odd values)
+          float seq = 0.0f;
+          if (j == 0)
+          {
+            const float* row = a.probs + (size_t) (base + g * Rg + it + u) * a.C;
+#pragma unroll 1
+            for (int c = 0; c < a.C; c++)
+            {
+              seq = __fadd_rn(seq, row[c]);
+            }
+          }
+          s = seq;
+        }
+        s = __shfl_sync(0xFFFFFFFFu, s, g * LG); // (uniform inside the sub-group either way)
+        const bool ok = idu[u] != INVALID_ID && s > 0.5f;
+        if (ok)
+        {
+          if (idu[u] != cur)
+          {
+            flush();
+            cur = idu[u];
+          }
+#pragma unroll
+          for (int p = 0; p < NP; p++)
+          {
+#pragma unroll
+            for (int k = 0; k < VW; k++)
+            {
+              if (KIND == SMESH_KIND_SUM)
+              {
+                acc[p][k] = __fadd_rn(acc[p][k], __fmul_rn(v[u][p][k], wu[u])); // acc += probs * w (MiscOps.h:83-93)
+              }
+              else
+              {
+                const int c = j + p * LG;
+                if (c < K)
+                {
+                  acc[p][k] = __fadd_rn(acc[p][k], neg_log_pow(v[u][p][k], wu[u]));
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    flush();
+  }
+}
+
+template <int KIND, int VW>
+static int launch_scatter_rows(const ScatterArgs& args, cudaStream_t stream)
+{
+  const int K = args.C / VW;
+  const int lg = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
+  const int np = (K + lg - 1) / lg;
+  int64_t blocks = (args.npix + 255) / 256;
+  const int64_t cap = (int64_t) num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) return SMESH_OK;
+  const unsigned nb = (unsigned) blocks;
+  if (lg == 8) scatter_rows_kernel<KIND, VW, 8, 1><<<nb, 256, 0, stream>>>(args);
+  else if (lg == 16) scatter_rows_kernel<KIND, VW, 16, 1><<<nb, 256, 0, stream>>>(args);
+  else if (np == 1) scatter_rows_kernel<KIND, VW, 32, 1><<<nb, 256, 0, stream>>>(args);
+  else if (np == 2) scatter_rows_kernel<KIND, VW, 32, 2><<<nb, 256, 0, stream>>>(args);
+  else if (np == 3) scatter_rows_kernel<KIND, VW, 32, 3><<<nb, 256, 0, stream>>>(args);
+  else if (np == 4) scatter_rows_kernel<KIND, VW, 32, 4><<<nb, 256, 0, stream>>>(args);
+  else
+  {
+    set_error("scatter_rows_kernel: class vector too wide (C=%d)", args.C);
+    return SMESH_ERR_UNSUPPORTED;
+  }
+  SMESH_LAUNCH_CHECK("scatter_rows_kernel");
+  return SMESH_OK;
+}
+
+// C >= 32 with 16 or more chunks per row and at most 4 per lane, rows aligned for the vector width (C % 4 == 0 with a 16-byte aligned image,
+// C % 2 == 0 with an 8-byte aligned one, any alignment for odd C)
+static bool rows_kernel_takes(const ScatterArgs& args, int& vw)
+{
+  static const bool off = getenv("SMESH_NO_ROWS") != nullptr;
+  if (off || args.C < 32)
+  {
+    return false;
+  }
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(args.probs);
+  vw = (args.C % 4 == 0 && (addr & 15) == 0) ? 4 : ((args.C % 2 == 0 && (addr & 7) == 0) ? 2 : 1);
+  // at least 16 chunks per row (full sub-groups; measured at C = 40, 10 chunks: 29 us against 25 us for the ring kernel)
+  return args.C / vw >= 16 && (args.C / vw + 31) / 32 <= 4;
+}
+
 // Fallback for shapes the ring cannot take (class vector too wide for shared memory, misaligned probability image):
 // one thread per pixel straight from global memory. Same arithmetic, no staging.
 template <int KIND>
@@ -1138,6 +1412,16 @@ static int launch_scatter(const ScatterArgs& args, cudaStream_t stream)
   RingConfig cfg;
   const bool aligned = (reinterpret_cast<uintptr_t>(args.probs) & 15) == 0;
   static const bool no_pair = getenv("SMESH_NO_PAIR") != nullptr;
+  if (KIND != SMESH_KIND_SUMMAX)
+  {
+    int vw = 1;
+    if (rows_kernel_takes(args, vw))
+    {
+      constexpr int K = KIND == SMESH_KIND_SUMMAX ? SMESH_KIND_SUM : KIND;
+      return vw == 4 ? launch_scatter_rows<K, 4>(args, stream)
+                     : (vw == 2 ? launch_scatter_rows<K, 2>(args, stream) : launch_scatter_rows<K, 1>(args, stream));
+    }
+  }
   if (aligned && ring_config(args.C, cfg))
   {
     if (KIND != SMESH_KIND_SUMMAX && !no_pair && (reinterpret_cast<uintptr_t>(args.ids) & 7) == 0)

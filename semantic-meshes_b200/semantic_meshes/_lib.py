@@ -21,6 +21,8 @@ SIGNATURES = {
     "smesh_raster_mesh_bytes": (_int, [_i64, _i64, ctypes.POINTER(_sz), ctypes.POINTER(_sz)]),
     "smesh_raster_mesh_build": (_int, [_vp, _i64, _vp, _i64, _vp, _sz, _vp, _sz, _vp]),
     "smesh_raster_render": (_int, [_vp, _sz, _i64, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _vp, _vp, _vp]),
+    "smesh_raster_render_counted": (_int, [_vp, _sz, _i64, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _vp, _vp, _vp, _u32,
+                                           _vp]),
     "smesh_fuse_padded_classes": (_int, [_int]),
     "smesh_fuse_add": (_int, [_int, _vp, _int, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _int, _i64, _f32, _vp, _u32,
                               _vp, _vp, _vp]),

@@ -50,9 +50,12 @@ class MeshAggregator:
         self._id_dtypes = _torch_id_dtypes(torch)
         # raw accumulator [P, Cpad] (mul: -log p), per-view pixel counters [P], flat id scratch (grown on demand)
         self._acc = torch.zeros((primitives, self._cpad), dtype=torch.float32, device=self.device)
-        self._counts = torch.zeros((max(primitives, 1),), dtype=torch.int32, device=self.device)
+        # two counter arrays, used alternately (epoch parity): a renderer may already be counting the next view into one
+        # (render(camera, count_into=...)) while this view's scatter still reads the other
+        self._counts2 = torch.zeros((2, max(primitives, 1)), dtype=torch.int32, device=self.device)
         self._ids32 = torch.empty((0,), dtype=torch.int32, device=self.device)
-        self._epoch = 0  # last count epoch handed out (see include/smesh.h: tagged per-view pixel counters)
+        self._epoch = 0      # last count epoch handed out (see include/smesh.h: tagged per-view pixel counters)
+        self._epoch_gen = 0  # bumped whenever the counters are zeroed: tokens of earlier counted renders become void
 
     # ---------------------------------------------------------------------------------------------------------------
     def _as_tensor(self, obj, what):
@@ -132,8 +135,18 @@ class MeshAggregator:
         """Zero the per-view pixel counters and start the count epochs over. Called automatically when the 8-bit epoch
         wraps; call it yourself at the start of any region you capture into a CUDA graph, so every replay sees the same
         epochs on clean counters."""
-        self._counts.zero_()
+        self._counts2.zero_()
         self._epoch = 0
+        self._epoch_gen += 1
+
+    def _counts_for(self, epoch):
+        return self._counts2[epoch & 1]
+
+    @property
+    def _counts(self):
+        """The counter array of the NEXT epoch to be handed out (tools that drive the C ABI stage by stage use it with
+        explicit epochs of one parity; `add` picks the array from the epoch itself)."""
+        return self._counts2[0]
 
     def _next_epochs(self, npix, n=1):
         """-> first of n consecutive count epochs for views of npix pixels (0 = untagged mode for huge images)."""
@@ -154,20 +167,34 @@ class MeshAggregator:
 
     # ---------------------------------------------------------------------------------------------------------------
     def add(self, primitive_indices, probs, weights=None):
-        """Fuse one view (ModelAggregator::add, Mesh.h:65-107)."""
+        """Fuse one view (ModelAggregator::add, Mesh.h:65-107). If `primitive_indices` comes from
+        `renderer.render(camera, count_into=self)` the per-face pixel counts are already in place and only the scatter
+        stage runs."""
         torch = self._torch
         ids, id_dtype, pr, wt = self._stage(primitive_indices, probs, weights)
         lay = self._layout(ids, pr, wt)
         if lay is None or self.primitives == 0:
             return
         pr, wt, n_outer, n_inner, ids_so, ids_si, w_so, w_si = lay
+        stream = torch.cuda.current_stream().cuda_stream
+        token = getattr(primitive_indices, "_smesh_counted", None)
+        if (token is not None and token[0] == id(self) and token[1] == self._epoch_gen and ids.dtype == torch.int32
+                and (ids_si == 1 or n_inner == 1) and (ids_so == n_inner or n_outer == 1)):
+            epoch = token[2]
+            with torch.cuda.device(self.device):
+                rc = _lib.lib.smesh_fuse_scatter(self._kind, ids.data_ptr(), pr.data_ptr(),
+                                                 wt.data_ptr() if wt is not None else None, n_outer * n_inner, self.classes,
+                                                 self.primitives, self.images_equal_weight,
+                                                 self._counts_for(epoch).data_ptr(), epoch, self._acc.data_ptr(), stream)
+            _lib.check(rc)
+            return
+        epoch = self._next_epochs(n_outer * n_inner)
         with torch.cuda.device(self.device):
             rc = _lib.lib.smesh_fuse_add(self._kind, ids.data_ptr(), id_dtype, ids_so, ids_si, pr.data_ptr(),
                                          wt.data_ptr() if wt is not None else None, w_so, w_si, n_outer, n_inner,
                                          self.classes, self.primitives, self.images_equal_weight,
-                                         self._counts.data_ptr(), self._next_epochs(n_outer * n_inner),
-                                         self._scratch(n_outer * n_inner).data_ptr(), self._acc.data_ptr(),
-                                         torch.cuda.current_stream().cuda_stream)
+                                         self._counts_for(epoch).data_ptr(), epoch,
+                                         self._scratch(n_outer * n_inner).data_ptr(), self._acc.data_ptr(), stream)
         _lib.check(rc)
 
     def add_batch(self, primitive_indices, probs, weights=None):
@@ -202,7 +229,7 @@ class MeshAggregator:
                     self._kind, nb, ids[done].data_ptr(), id_dtype, ids.stride(0), ids_so, ids_si, pr[done].data_ptr(),
                     pr.stride(0), wt[done].data_ptr() if wt is not None else None, wt.stride(0) if wt is not None else 0,
                     w_so, w_si, n_outer, n_inner, self.classes, self.primitives, self.images_equal_weight,
-                    self._counts.data_ptr(), epoch0, self._scratch(npix).data_ptr(), self._acc.data_ptr(),
+                    self._counts_for(0).data_ptr(), epoch0, self._scratch(npix).data_ptr(), self._acc.data_ptr(),
                     torch.cuda.current_stream().cuda_stream)
             _lib.check(rc)
             done += nb

@@ -67,13 +67,18 @@ class TriangleRenderer:
             self._workspace_res = (W, H)
         return self._workspace
 
-    def render(self, camera, capsule=False):
+    def render(self, camera, capsule=False, count_into=None):
         """-> (primitive_indices, depth): torch tensors on the GPU, shapes (W, H).
 
         primitive_indices is int32 holding the reference's uint32 bit pattern (background 0xFFFFFFFF reads as -1; torch
         has few uint32 ops) - `MeshAggregator.add` takes it as is. With capsule=True both are returned as DLPack
         capsules named "dltensor", exactly what the reference returns (Renderer.h:37-41), for
         `tf.experimental.dlpack.from_dlpack` style consumers.
+
+        count_into=aggregator (extension): the pass that writes the index image also leaves the per-face pixel counts
+        of this view in the aggregator's counters, and `aggregator.add(primitive_indices, probs)` of THIS index image then
+        skips its count pass. The aggregator must be over the faces of this mesh; between such a render and its add at
+        most one other counted render may be issued (two counter arrays).
         """
         if not isinstance(camera, Camera):
             raise TypeError("render expects a semantic_meshes.data.Camera")
@@ -81,16 +86,31 @@ class TriangleRenderer:
         W, H = camera.resolution
         if W < 1 or H < 1:
             raise ValueError("render: empty resolution")
+        epoch = 0
+        if count_into is not None:
+            if count_into.primitives != self._F or count_into.device != self.device:
+                raise ValueError("render(count_into=...): the aggregator must hold one row per face of this mesh, on this device")
+            if W * H < (1 << 24) and self._F > 0 and not capsule:
+                epoch = count_into._next_epochs(W * H)
         with torch.cuda.device(self.device):
             ws = self._ensure_workspace(W, H)
             idx = torch.empty((W, H), dtype=torch.int32, device=self.device)
             depth = torch.empty((W, H), dtype=torch.float32, device=self.device)
             R, t = camera.rotation, camera.translation
             f, c = camera.focal_lengths, camera.principal_point
-            rc = _lib.lib.smesh_raster_render(self._mesh.data_ptr(), self._mesh.numel(), self._V, self._F, R.ctypes.data,
-                                              t.ctypes.data, f.ctypes.data, c.ctypes.data, W, H, ws.data_ptr(), ws.numel(),
-                                              idx.data_ptr(), depth.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            stream = torch.cuda.current_stream().cuda_stream
+            if epoch != 0:
+                rc = _lib.lib.smesh_raster_render_counted(self._mesh.data_ptr(), self._mesh.numel(), self._V, self._F,
+                                                          R.ctypes.data, t.ctypes.data, f.ctypes.data, c.ctypes.data, W, H,
+                                                          ws.data_ptr(), ws.numel(), idx.data_ptr(), depth.data_ptr(),
+                                                          count_into._counts_for(epoch).data_ptr(), epoch, stream)
+            else:
+                rc = _lib.lib.smesh_raster_render(self._mesh.data_ptr(), self._mesh.numel(), self._V, self._F, R.ctypes.data,
+                                                  t.ctypes.data, f.ctypes.data, c.ctypes.data, W, H, ws.data_ptr(),
+                                                  ws.numel(), idx.data_ptr(), depth.data_ptr(), stream)
         _lib.check(rc)
+        if epoch != 0:
+            idx._smesh_counted = (id(count_into), count_into._epoch_gen, epoch)
         if capsule:
             from torch.utils.dlpack import to_dlpack
             return to_dlpack(idx.view(torch.uint32)), to_dlpack(depth)

@@ -291,6 +291,52 @@ def test_add_on_rendered_ids(sm):
     assert_acc_close("sum", agg.state().cpu().numpy(), ref.acc)
 
 
+@pytest.mark.parametrize("kind", ["sum", "mul"])
+@pytest.mark.parametrize("C", [32, 33, 40, 64, 66, 150, 257, 512])
+def test_wide_class_vectors(sm, kind, C):
+    """C >= 32 takes scatter_rows_kernel (lanes across the classes of a pixel): sub-groups of 8 / 16 / 32 lanes, one to
+    four chunks per lane, 128-bit / 64-bit / scalar rows (C % 4, C % 2, odd C, an image that starts 8 or 4 bytes off a
+    16-byte boundary), weights, and the gate: rows whose sum sits exactly at, just below and just above 0.5, rows with
+    negative entries and rows with a NaN must be accepted / rejected exactly as the sequential float sum decides."""
+    import torch
+    W, H, P = 37, 29, 300
+    rng = np.random.default_rng(C)
+    agg = sm.fusion.MeshAggregator(primitives=P, classes=C, aggregator=kind)
+    ref = oracle.Aggregator(P, C, kind)
+    for v in range(3):
+        ids, probs = make_view(rng, W, H, C, P, block=(1, 3, 6)[v])
+        flat = probs.reshape(-1, C)
+        # gate edge cases on a tenth of the pixels
+        pick = rng.choice(flat.shape[0], flat.shape[0] // 10, replace=False)
+        for k, i in enumerate(pick):
+            row = np.abs(rng.normal(size=C)).astype(np.float32)
+            mode = k % 5
+            if mode == 0:
+                row *= np.float32(0.5) / row.sum(dtype=np.float32)             # at the threshold (either side by rounding)
+            elif mode == 1:
+                row *= np.float32(0.5 * (1 - 3e-4)) / row.sum(dtype=np.float32)
+            elif mode == 2:
+                row *= np.float32(0.5 * (1 + 3e-4)) / row.sum(dtype=np.float32)
+            elif mode == 3:
+                row[rng.integers(0, C)] *= -1                                  # a negative entry
+                row *= np.float32(0.7) / max(abs(float(row.sum())), 1e-3)
+            elif kind == "sum":
+                row[rng.integers(0, C)] = np.nan                               # NaN: the gate fails, the pixel is skipped
+            flat[i] = row
+        if kind == "mul":
+            np.abs(flat, out=flat)                                             # log of a negative probability is not defined
+        wts = (rng.random((W, H)) * 2).astype(np.float32) if v == 1 else None
+        pr = torch.from_numpy(probs).cuda()
+        if v == 2:                                                             # a view that starts 4 or 8 bytes off
+            off = 1 if C % 2 else 2
+            buf = torch.empty(probs.size + 4, dtype=torch.float32, device="cuda")
+            buf[off:off + probs.size] = pr.reshape(-1)
+            pr = buf[off:off + probs.size].view(W, H, C)
+        agg.add(torch.from_numpy(ids.view(np.int32)).cuda(), pr, None if wts is None else torch.from_numpy(wts).cuda())
+        ref.add(ids, probs, wts)
+    assert_acc_close(kind, agg.state().cpu().numpy(), ref.acc)
+
+
 def test_count_epoch_wraparound(sm):
     """The per-view pixel counters are tagged with an 8-bit epoch instead of being cleared (include/smesh.h); 600 views
     cross the wrap twice, and the face -> pixel-count mapping changes every view."""

@@ -313,6 +313,44 @@ def test_render_then_add_pipeline(sm):
     np.testing.assert_allclose(agg.get(), ref.get(), rtol=1e-5, atol=1e-7)
 
 
+def test_counted_render_feeds_add(sm):
+    """render(camera, count_into=aggregator) leaves the per-face pixel counts of the view in the aggregator:
+    add() of that index image then runs the scatter stage alone and must give exactly what the plain render + add gives -
+    also when two counted renders are in flight, when the counters were restarted in between (the token is void, add
+    recounts) and for the mul aggregator."""
+    import torch
+    from semantic_meshes import synthetic
+    W, H, C = 192, 160, 19
+    mesh = synthetic.mesh("terrain", 9000, seed=8)
+    renderer = sm.render.triangles(mesh)
+    P = renderer.getPrimitivesNum()
+    cams = synthetic.terrain_cameras(5, W, H, 9000, tris_per_view=3500, seed=13)
+    preds = [synthetic.predictions_torch(W, H, C, seed=70 + v, device="cuda") for v in range(len(cams))]
+    for kind in ("sum", "mul"):
+        plain, fused = sm.fusion.MeshAggregator(P, C, kind), sm.fusion.MeshAggregator(P, C, kind)
+        for v, cam in enumerate(cams):
+            idx, _ = renderer.render(cam)
+            plain.add(idx, preds[v])
+        # two counted renders ahead of their adds
+        i0, _ = renderer.render(cams[0], count_into=fused)
+        i1, _ = renderer.render(cams[1], count_into=fused)
+        assert hasattr(i0, "_smesh_counted") and i0._smesh_counted[2] != i1._smesh_counted[2]
+        fused.add(i0, preds[0])
+        fused.add(i1, preds[1])
+        i2, _ = renderer.render(cams[2], count_into=fused)
+        fused.restart_epochs()                       # voids the token: add() must count again itself
+        fused.add(i2, preds[2])
+        for v in (3, 4):
+            iv, _ = renderer.render(cams[v], count_into=fused)
+            fused.add(iv, preds[v])
+        a, b = plain.state().cpu().numpy(), fused.state().cpu().numpy()
+        fin = np.isfinite(a)
+        assert np.array_equal(fin, np.isfinite(b))
+        np.testing.assert_allclose(b[fin], a[fin], rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        renderer.render(cams[0], count_into=sm.fusion.MeshAggregator(P + 1, C))
+
+
 def test_overlapped_pipeline_matches_sequential(sm):
     """pipeline.ViewPipeline (render of view v+1 on a second stream while view v is fused) == the sequential loop."""
     import torch
@@ -331,8 +369,11 @@ def test_overlapped_pipeline_matches_sequential(sm):
         seq.add(idx, preds[v])
         ids_seq.append(idx.clone())
     for rep in range(3):  # repeated: stream hand-over between runs
-        kept = ViewPipeline(renderer, ovl).run(cams, preds, keep_indices=True) if rep == 0 else pipe.run(cams, preds, keep_indices=True)
-        pipe = ViewPipeline(renderer, ovl) if rep == 0 else pipe
+        if rep == 0:
+            pipe = ViewPipeline(renderer, ovl)
+        elif rep == 2:
+            pipe = ViewPipeline(renderer, ovl, fused_count=True)   # counts taken in the render pass (N2)
+        kept = pipe.run(cams, preds, keep_indices=True)
         torch.cuda.synchronize()
         for a, b in zip(kept, ids_seq):
             assert torch.equal(a, b)
