@@ -185,6 +185,22 @@ int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id_dtype, int
  */
 int smesh_fuse_get(int kind, const float* acc, int64_t P, int C, float* out, void* stream);
 
+/*
+ * What follows get() in the reference's own pipeline.
+ *
+ * smesh_fuse_labels: per-face label from the distribution smesh_fuse_get returned (dist float32[P][C]), exactly
+ * python/scripts/colorize_mesh.py:82-88: -1 ("no annotation") if the row sums to less than dont_care_threshold (0.9 in the
+ * script), else the first class of maximal probability (tf.argmax). labels_out int32[P].
+ *
+ * smesh_fuse_render: ModelRenderer::render (include/semantic_meshes/fusion/Mesh.h:24-43), the gather-back of per-face
+ * annotations into an image: out[i] = annotations[ids32[i]] if ids32[i] < P else background, elements of elem_bytes
+ * bytes (labels: 4, colours: 3, distributions: 4*C); annotations [P], background one element, out [n_pix], all on the
+ * device.
+ */
+int smesh_fuse_labels(const float* dist, int64_t P, int C, float dont_care_threshold, int32_t* labels_out, void* stream);
+int smesh_fuse_render(const void* annotations, int64_t P, int elem_bytes, const uint32_t* ids32, int64_t n_pix,
+                      const void* background, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

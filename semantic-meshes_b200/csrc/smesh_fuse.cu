@@ -1750,3 +1750,111 @@ extern "C" int smesh_fuse_get(int kind, const float* acc, int64_t P, int C, floa
   SMESH_LAUNCH_CHECK("get_kernel");
   return SMESH_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// What follows get() in the reference's pipeline: per-face labels and the gather-back of per-face
+// annotations into an image.
+// ---------------------------------------------------------------------------------------------------------------------
+
+namespace smesh {
+namespace fuse {
+
+// python/scripts/colorize_mesh.py:82-88 on the distribution get() returns: a face whose distribution sums to less than
+// the threshold received no annotation (-1); otherwise the FIRST class of maximal probability (tf.argmax).
+__global__ void __launch_bounds__(256) labels_kernel(const float* __restrict__ dist, int64_t P, int C, float threshold,
+                                                     int32_t* __restrict__ labels)
+{
+  const int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P)
+  {
+    return;
+  }
+  const float* row = dist + (size_t) r * C;
+  float sum = 0.0f, best = row[0];
+  int best_c = 0;
+  for (int c = 0; c < C; c++)
+  {
+    const float v = row[c];
+    sum = __fadd_rn(sum, v);
+    if (v > best)
+    {
+      best = v;
+      best_c = c;
+    }
+  }
+  labels[r] = sum < threshold ? -1 : best_c;
+}
+
+// ModelRenderer::render (include/semantic_meshes/fusion/Mesh.h:24-43): dest(pixel) = annotations(primitive) if the
+// primitive index is valid, else background. Elements are `words` 32-bit words (or `bytes` bytes when words == 0).
+__global__ void __launch_bounds__(256) gather_kernel(const unsigned char* __restrict__ annotations, int64_t P, int words,
+                                                     int bytes, const uint32_t* __restrict__ ids, int64_t npix,
+                                                     const unsigned char* __restrict__ background,
+                                                     unsigned char* __restrict__ out)
+{
+  const int64_t per = words > 0 ? words : bytes;
+  const int64_t total = npix * per;
+  for (int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t) gridDim.x * blockDim.x)
+  {
+    const int64_t i = t / per, k = t - i * per;
+    const uint32_t id = ids[i];
+    const bool valid = (int64_t) id < P;
+    if (words > 0)
+    {
+      const uint32_t* src = valid ? reinterpret_cast<const uint32_t*>(annotations) + (size_t) id * words
+                                  : reinterpret_cast<const uint32_t*>(background);
+      reinterpret_cast<uint32_t*>(out)[t] = src[k];
+    }
+    else
+    {
+      const unsigned char* src = valid ? annotations + (size_t) id * bytes : background;
+      out[t] = src[k];
+    }
+  }
+}
+
+} // namespace fuse
+} // namespace smesh
+
+extern "C" int smesh_fuse_labels(const float* dist, int64_t P, int C, float dont_care_threshold, int32_t* labels_out,
+                                 void* stream_v)
+{
+  if (P < 0 || C < 1 || (P > 0 && (!dist || !labels_out)))
+  {
+    set_error("smesh_fuse_labels: invalid argument");
+    return SMESH_ERR_INVALID_ARGUMENT;
+  }
+  if (P > 0)
+  {
+    labels_kernel<<<(unsigned) ((P + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(dist, P, C, dont_care_threshold,
+                                                                                                labels_out);
+    SMESH_LAUNCH_CHECK("labels_kernel");
+  }
+  return SMESH_OK;
+}
+
+extern "C" int smesh_fuse_render(const void* annotations, int64_t P, int elem_bytes, const uint32_t* ids32, int64_t n_pix,
+                                 const void* background, void* out, void* stream_v)
+{
+  if (P < 0 || elem_bytes < 1 || n_pix < 0 || (n_pix > 0 && (!ids32 || !background || !out)) || (P > 0 && !annotations))
+  {
+    set_error("smesh_fuse_render: invalid argument");
+    return SMESH_ERR_INVALID_ARGUMENT;
+  }
+  if (n_pix == 0)
+  {
+    return SMESH_OK;
+  }
+  const bool word_aligned = elem_bytes % 4 == 0 && ((reinterpret_cast<uintptr_t>(annotations) | reinterpret_cast<uintptr_t>(background) |
+                                                      reinterpret_cast<uintptr_t>(out)) & 3) == 0;
+  const int words = word_aligned ? elem_bytes / 4 : 0;
+  const int64_t total = n_pix * (words > 0 ? words : elem_bytes);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t) num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  gather_kernel<<<(unsigned) blocks, 256, 0, static_cast<cudaStream_t>(stream_v)>>>(
+    static_cast<const unsigned char*>(annotations), P, words, elem_bytes, ids32, n_pix, static_cast<const unsigned char*>(background),
+    static_cast<unsigned char*>(out));
+  SMESH_LAUNCH_CHECK("gather_kernel");
+  return SMESH_OK;
+}

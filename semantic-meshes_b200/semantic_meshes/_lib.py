@@ -32,6 +32,8 @@ SIGNATURES = {
     "smesh_fuse_add_batch": (_int, [_int, _i64, _vp, _int, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64,
                                     _int, _i64, _f32, _vp, _u32, _vp, _vp, _vp]),
     "smesh_fuse_get": (_int, [_int, _vp, _i64, _int, _vp, _vp]),
+    "smesh_fuse_labels": (_int, [_vp, _i64, _int, _f32, _vp, _vp]),
+    "smesh_fuse_render": (_int, [_vp, _i64, _int, _vp, _i64, _vp, _vp, _vp]),
 }
 
 if not os.path.exists(LIB_PATH):

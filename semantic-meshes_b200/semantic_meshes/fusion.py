@@ -250,6 +250,60 @@ class MeshAggregator:
         return out if device else out.cpu().numpy()
 
     # ---------------------------------------------------------------------------------------------------------------
+    # what the reference's scripts do with get(), on the device
+    def labels(self, dont_care_threshold=0.9, device=False):
+        """Per-primitive class index (python/scripts/colorize_mesh.py:82-88): argmax of get(), -1 where the primitive
+        received no annotation (its distribution sums to less than dont_care_threshold). int32 (P,), numpy by default."""
+        torch = self._torch
+        dist = self.get(device=True)
+        out = torch.empty((self.primitives,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib.smesh_fuse_labels(dist.data_ptr(), self.primitives, self.classes, float(dont_care_threshold),
+                                            out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc)
+        return out if device else out.cpu().numpy()
+
+    def colors(self, class_to_color, dont_care_threshold=0.9, device=False):
+        """Per-primitive colour for `data.Ply.save` (colorize_mesh.py:86-92): class_to_color[label], black where the
+        primitive has no annotation. class_to_color: (classes, 3) uint8. uint8 (P, 3)."""
+        torch = self._torch
+        table = self._as_tensor(np.ascontiguousarray(class_to_color, dtype=np.uint8), "class_to_color")
+        if tuple(table.shape) != (self.classes, 3):
+            raise ValueError("class_to_color must have shape (classes, 3)")
+        lab = self.labels(dont_care_threshold, device=True).long()
+        col = table[lab.clamp(min=0)]
+        col[lab < 0] = 0
+        return col if device else col.cpu().numpy()
+
+    def render(self, primitive_indices, annotations, background):
+        """ModelRenderer::render (include/semantic_meshes/fusion/Mesh.h:24-43): the image of per-primitive annotations,
+        out[x, y] = annotations[primitive_indices[x, y]] where that index is a primitive, else background.
+        annotations: (P,) or (P, K) array of any 1-, 2-, 4-byte ... dtype (labels, colours, distributions); background:
+        one element. Returns a torch CUDA tensor of shape (W, H) or (W, H, K)."""
+        torch = self._torch
+        ids = self._as_tensor(primitive_indices, "primitive_indices")
+        id_dtype = self._id_dtypes.get(ids.dtype)
+        if id_dtype is None or ids.dim() != 2:
+            raise ValueError(_NONE_MATCHED + "primitive_indices must be a rank-2 uint32/int32/uint64/int64 array")
+        ann = self._as_tensor(annotations, "annotations").contiguous()
+        if ann.dim() not in (1, 2) or ann.shape[0] != self.primitives:
+            raise ValueError("annotations must have one row per primitive")
+        bg = torch.as_tensor(background, dtype=ann.dtype, device=self.device).reshape(ann.shape[1:]).contiguous()
+        W, H = ids.shape
+        if id_dtype in (_lib.ID_U64, _lib.ID_I64):
+            ids32 = torch.where((ids >= 0) & (ids < self.primitives), ids, torch.full_like(ids, -1)).to(torch.int32)
+        else:
+            ids32 = ids.view(torch.int32) if ids.dtype != torch.int32 else ids
+        ids32 = ids32.contiguous()
+        out = torch.empty((W, H) + tuple(ann.shape[1:]), dtype=ann.dtype, device=self.device)
+        elem_bytes = ann.element_size() * (ann.shape[1] if ann.dim() == 2 else 1)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib.smesh_fuse_render(ann.data_ptr(), self.primitives, elem_bytes, ids32.data_ptr(), W * H,
+                                            bg.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc)
+        return out
+
+    # ---------------------------------------------------------------------------------------------------------------
     # extensions for view-sharded multi-GPU runs and checkpointing
     def allreduce(self, group=None):
         """Sum the raw accumulators of all ranks in place (one NCCL all-reduce of P x Cpad floats). Every aggregator

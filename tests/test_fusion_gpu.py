@@ -337,6 +337,38 @@ def test_wide_class_vectors(sm, kind, C):
     assert_acc_close(kind, agg.state().cpu().numpy(), ref.acc)
 
 
+def test_labels_colors_and_gather_back(sm):
+    """what the reference's scripts do after get() - labels / colours per primitive
+    (python/scripts/colorize_mesh.py:82-92) and ModelRenderer::render (Mesh.h:24-43), the image of per-primitive
+    annotations - against the same few lines of numpy."""
+    import torch
+    W, H, C, P = 53, 47, 7, 90
+    rng = np.random.default_rng(5)
+    agg = sm.fusion.MeshAggregator(primitives=P, classes=C)
+    ids, probs = make_view(rng, W, H, C, P // 2, block=3)       # the upper half of the primitives is never seen
+    agg.add(torch.from_numpy(ids.view(np.int32)).cuda(), torch.from_numpy(probs).cuda())
+    dist = agg.get()
+    exp_labels = np.where(dist.sum(-1, dtype=np.float32) < 0.9, -1, dist.argmax(-1)).astype(np.int32)
+    labels = agg.labels()
+    assert labels.dtype == np.int32 and np.array_equal(labels, exp_labels) and (labels == -1).sum() >= P // 2 - 2
+    table = rng.integers(1, 255, size=(C, 3)).astype(np.uint8)
+    colors = agg.colors(table)
+    exp_colors = np.where(exp_labels[:, None] < 0, 0, table[np.maximum(exp_labels, 0)]).astype(np.uint8)
+    assert colors.dtype == np.uint8 and np.array_equal(colors, exp_colors)
+    valid = ids < P
+    for ann, bg in ((exp_labels, -7), (exp_colors, (9, 8, 7)), (dist, np.full(C, 0.25, np.float32)),
+                    (rng.integers(0, 200, P).astype(np.uint8), 255)):
+        img = agg.render(torch.from_numpy(ids.view(np.int32)).cuda(), ann, bg).cpu().numpy()
+        exp = np.empty((W, H) + ann.shape[1:], dtype=ann.dtype)
+        exp[valid] = ann[ids[valid]]
+        exp[~valid] = np.asarray(bg, dtype=ann.dtype)
+        assert img.dtype == ann.dtype and np.array_equal(img, exp)
+    img64 = agg.render(torch.from_numpy(ids.astype(np.int64)).cuda(), exp_labels, -7).cpu().numpy()
+    ids_wide = ids.astype(np.int64)
+    exp = np.where(ids_wide < P, exp_labels[np.minimum(ids_wide, P - 1)], -7)
+    assert np.array_equal(img64, exp)
+
+
 def test_count_epoch_wraparound(sm):
     """The per-view pixel counters are tagged with an 8-bit epoch instead of being cleared (include/smesh.h); 600 views
     cross the wrap twice, and the face -> pixel-count mapping changes every view."""
