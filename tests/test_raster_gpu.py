@@ -267,6 +267,24 @@ def test_camera_plane_straddlers(sm, tilt_deg):
         assert (gi != BG).mean() > 0.3
 
 
+@pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg5"])
+def test_full_size_configs_bit_exact(sm, name):
+    """The BASELINE.json shapes at FULL size (cfg3: 2 M triangles, 2048x1024; cfg5: 5 M triangles, 1280x720, a tilted
+    camera whose plane cuts the mesh) - one view each, index and depth bit-exact against the oracle, which tests every
+    pixel of every bounding box like the reference (about 1e8 - 1e9 pixel tests on the host cores)."""
+    import bench
+    cfg = bench.CONFIGS[name]
+    mesh, cams = bench.build_scene(cfg, 0, 2)
+    renderer = sm.render.triangles(mesh)
+    cam = cams[1]
+    gi, gd, oi, od = render_both(sm, mesh, cam, renderer)
+    assert_bit_exact(gi, gd, oi, od)
+    assert (gi != BG).mean() > 0.9
+    # properties that need no oracle: ids are faces of the mesh, every depth is finite where something was hit
+    hit = gi != BG
+    assert gi[hit].max() < mesh.faces.shape[0] and np.isfinite(gd[hit]).all() and np.isinf(gd[~hit]).all()
+
+
 def test_intrinsics_change_rebuilds_ray_table(sm):
     """The per-pixel ray normalisation is cached per intrinsics inside the renderer's workspace."""
     from semantic_meshes import synthetic
