@@ -236,7 +236,6 @@ struct ScatterArgs
   int stages;
   uint32_t count_mask;     // COUNT_MASK with a tagged epoch, 0xFFFFFFFF without
   uint32_t run_cap;        // power of two <= 32: runs of equal ids are cut every run_cap lanes
-  uint32_t debug_skip;     // profiling only: 1 = no reductions, 2 = no run reduction, 4 = no per-pixel work at all
 
   float iew;
 };
@@ -538,7 +537,7 @@ __global__ void __launch_bounds__(288) scatter_kernel(ScatterArgs a)
 // finished chain of its right neighbour to T. Run heads (S or T) issue the 128-bit reductions.
 // ---------------------------------------------------------------------------------------------------------------------
 
-template <int KIND, int CT, int TMA_FLUSH>
+template <int KIND, int CT>
 __global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
 {
   static_assert(CT >= 1 && CT <= CH, "pair kernel holds 2 x CT values in registers");
@@ -554,7 +553,7 @@ __global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + stage_floats * stages);
   uint64_t* empty_bar = full_bar + stages;
-  // TMA_FLUSH: per consumer warp 2 x 32 row slots of Cpad floats (run sums staged for cp.reduce.async.bulk)
+  // per consumer warp 64 row slots of Cpad floats + their face ids: the run sums staged for the coalesced flush
   float* flush_base = reinterpret_cast<float*>(empty_bar + stages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -657,15 +656,6 @@ __global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
 
     mbar_wait(full_bar + s, parity);
     const float2* row2 = reinterpret_cast<const float2*>(stage_ptr + stage_floats * s);
-    if (a.debug_skip & 4u)
-    {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar + s);
-      if (++s == stages) { s = 0; parity ^= 1u; }
-      id = id1; id1 = id2; wt = wt1; wt1 = wt2; n = n1;
-      continue;
-    }
-
     // ---- both pixels' class vectors: 2C contiguous floats, C 64-bit loads ----
     float ab[2 * C];
 #pragma unroll
@@ -735,7 +725,7 @@ __global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
     const int maxlen = (int) __reduce_max_sync(0xFFFFFFFFu, (unsigned) (end - lane));
 
     // segmented suffix sum of S over the chain (log2(longest chain) shuffle rounds, warp-uniform)
-    for (int d = 1; d < ((a.debug_skip & 2u) ? 0 : maxlen); d <<= 1)
+    for (int d = 1; d < maxlen; d <<= 1)
     {
       const bool take = lane + d < end;
 #pragma unroll
@@ -762,14 +752,13 @@ __global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
       }
     }
     // run heads own the sums and add them to the padded accumulator row (Cpad floats, 16-byte aligned)
-    if constexpr (TMA_FLUSH == 3)
     {
       // Coalesced flush: the run sums are compacted into shared memory rows, then every group of 5 adjacent lanes adds
       // one 80-byte row with a single red.global.add.v4.f32 instruction (6 rows per warp instruction): the L2 receives
       // whole-sector requests (3 per row instead of 5 half-sector ones) and no lane idles in a per-row loop.
       float* rows = flush_base + (size_t) cw * (64 * Cpad + 64);
       uint32_t* row_id = reinterpret_cast<uint32_t*>(rows + 64 * Cpad);
-      const bool doS = headS && !(a.debug_skip & 1u), doT = hasT && !(a.debug_skip & 1u);
+      const bool doS = headS, doT = hasT;
       const uint32_t smask = __ballot_sync(0xFFFFFFFFu, doS), tmask = __ballot_sync(0xFFFFFFFFu, doT);
       const uint32_t below = (1u << lane) - 1u;
       const int nS = __popc(smask), nrows = nS + __popc(tmask);
@@ -808,81 +797,6 @@ __global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
       }
       __syncwarp();
     }
-    else if constexpr (TMA_FLUSH != 0)
-    {
-      // staged in shared memory and handed to the TMA unit as ONE reduce-add of the whole row per run: the L2 sees
-      // full-sector requests instead of five 16-byte ones, and the LSU is not involved
-      constexpr int SLOTS = TMA_FLUSH == 2 ? 32 : 64; // staged rows per warp (S only in mixed mode)
-      float* slotS = flush_base + ((size_t) cw * SLOTS + lane) * Cpad;
-      float* slotT = slotS + 32 * Cpad;
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // this lane's previous rows have been read
-      const bool dbg_quarter = (a.debug_skip & 8u) && (lane & 3) != 0; // profiling: only a quarter of the rows
-      const bool doS = headS && !(a.debug_skip & 1u) && !dbg_quarter, doT = hasT && !(a.debug_skip & 1u) && !dbg_quarter;
-      if (doS)
-      {
-#pragma unroll
-        for (int j = 0; j < NCHUNK; j++)
-        {
-          *reinterpret_cast<float4*>(slotS + 4 * j) = make_float4(A[4 * j], A[4 * j + 1], A[4 * j + 2], A[4 * j + 3]);
-        }
-      }
-      if (doT && TMA_FLUSH == 2)
-      {
-        // mixed mode: the T rows go through the LSU (red.v4) while the S rows go through the TMA unit
-        float* dst = a.acc + (size_t) id.y * Cpad;
-#pragma unroll
-        for (int j = 0; j < NCHUNK; j++)
-        {
-          red_add_v4(dst + 4 * j, B[4 * j], B[4 * j + 1], B[4 * j + 2], B[4 * j + 3]);
-        }
-      }
-      if (doT && TMA_FLUSH == 1)
-      {
-#pragma unroll
-        for (int j = 0; j < NCHUNK; j++)
-        {
-          *reinterpret_cast<float4*>(slotT + 4 * j) = make_float4(B[4 * j], B[4 * j + 1], B[4 * j + 2], B[4 * j + 3]);
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (doS && !(a.debug_skip & 16u))
-      {
-        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(
-                       a.acc + (size_t) id.x * Cpad),
-                     "r"(smem_u32(slotS)), "n"(Cpad * 4)
-                     : "memory");
-      }
-      if (doT && TMA_FLUSH == 1 && !(a.debug_skip & 16u))
-      {
-        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(
-                       a.acc + (size_t) id.y * Cpad),
-                     "r"(smem_u32(slotT)), "n"(Cpad * 4)
-                     : "memory");
-      }
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-    else
-    {
-      // one 128-bit reduction per 4 classes
-      if (headS && !(a.debug_skip & 1u))
-      {
-        float* dst = a.acc + (size_t) id.x * Cpad;
-#pragma unroll
-        for (int j = 0; j < NCHUNK; j++)
-        {
-          red_add_v4(dst + 4 * j, A[4 * j], A[4 * j + 1], A[4 * j + 2], A[4 * j + 3]);
-        }
-      }
-      if (hasT && !(a.debug_skip & 1u))
-      {
-        float* dst = a.acc + (size_t) id.y * Cpad;
-#pragma unroll
-        for (int j = 0; j < NCHUNK; j++)
-        {
-          red_add_v4(dst + 4 * j, B[4 * j], B[4 * j + 1], B[4 * j + 2], B[4 * j + 3]);
-        }
-      }
-    }
 
     __syncwarp();
     if (lane == 0)
@@ -897,10 +811,6 @@ __global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
     id = id1; id1 = id2;
     wt = wt1; wt1 = wt2;
     n = n1;
-  }
-  if constexpr (TMA_FLUSH == 1 || TMA_FLUSH == 2)
-  {
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 }
 
@@ -1367,15 +1277,14 @@ static PairConfig pair_config()
   return cfg;
 }
 
-template <int KIND, int CT, int TMA_FLUSH>
+template <int KIND, int CT>
 static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
 {
   ScatterArgs args = args_in;
   const PairConfig cfg = pair_config();
   const size_t smem = (size_t) cfg.stages * cfg.consumer_warps * 64 * CT * 4 + (size_t) cfg.stages * 16 +
-                      (size_t) cfg.consumer_warps * (TMA_FLUSH == 1 ? 64 : (TMA_FLUSH == 2 ? 32 : 0)) * ((CT + 3) & ~3) * 4 +
-                      (TMA_FLUSH == 3 ? (size_t) cfg.consumer_warps * (64 * ((CT + 3) & ~3) + 64) * 4 : 0);
-  auto kernel = scatter_pair_kernel<KIND, CT, TMA_FLUSH>;
+                      (size_t) cfg.consumer_warps * (64 * ((CT + 3) & ~3) + 64) * 4; // flush rows + their face ids
+  auto kernel = scatter_pair_kernel<KIND, CT>;
   static thread_local size_t configured_smem = 0;
   static thread_local int blocks_per_sm = 0;
   static thread_local int configured_threads = 0;
@@ -1433,11 +1342,8 @@ static int launch_scatter(const ScatterArgs& args, cudaStream_t stream)
       {
         case 19:
         {
-          static const int tma_flush = getenv("SMESH_TMA_FLUSH") ? atoi(getenv("SMESH_TMA_FLUSH")) : 3;
           constexpr int K = KIND == SMESH_KIND_SUMMAX ? SMESH_KIND_SUM : KIND;
-          if (tma_flush == 2) return launch_scatter_pair<K, 19, 2>(args, stream);
-          if (tma_flush == 3) return launch_scatter_pair<K, 19, 3>(args, stream);
-          return tma_flush ? launch_scatter_pair<K, 19, 1>(args, stream) : launch_scatter_pair<K, 19, 0>(args, stream);
+          return launch_scatter_pair<K, 19>(args, stream);
         }
         default: break;
       }
@@ -1518,7 +1424,6 @@ static ScatterArgs make_scatter_args(const uint32_t* ids32, const float* probs, 
   args.stages = 0;
   args.count_mask = epoch != 0 ? COUNT_MASK : 0xFFFFFFFFu;
   args.run_cap = scatter_run_cap();
-  args.debug_skip = getenv("SMESH_DEBUG_SKIP") ? (uint32_t) atoi(getenv("SMESH_DEBUG_SKIP")) : 0u;
   args.iew = iew;
   return args;
 }
