@@ -337,7 +337,7 @@ def run_ours(args, cfg):
         "mpixel_face_scatters_per_s": value * float(np.mean(accepted)) / 1e6,
         "stages": {"render_ms_per_view": render_ms, "add_ms_per_view": add_ms, "scatter_kernel_ms": scatter_ms,
                    "render_views_per_s": 1e3 / render_ms, "add_views_per_s": 1e3 / add_ms, "allreduce_ms": allreduce_ms},
-        "roofline": {"bound": "hbm", "kernel": "smesh::fuse::scatter_kernel", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "smesh::fuse::scatter_pair_kernel" if C == 19 else "smesh::fuse::scatter kernel of this C", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_alg, "input_only_frac": bytes_inputs / (scatter_ms * 1e-3) / 1e9 / peak},
         "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": int(B * npix * C * 4),
