@@ -111,6 +111,28 @@ int smesh_raster_render_counted(const void* mesh, size_t mesh_bytes, int64_t V, 
                                 size_t workspace_bytes, uint32_t* idx_out, float* depth_out, uint32_t* counts,
                                 uint32_t count_epoch, void* stream);
 
+/*
+ * Texel renderer: replaces semantic_meshes::render::TexturedTriangleRenderer
+ * (include/semantic_meshes/render/TexturedTriangleRenderer.h), the `render.texels(...)` of
+ * python/semantic_meshes/src/Render.cu:20-23: primitives are the TEXELS of per-triangle textures instead of the triangles.
+ *
+ * smesh_texels_prepare = its constructor (:86-176), on the HOST like the reference's (its decisions hang on host float
+ * arithmetic, glibc acosf included): per triangle the texture resolution from the largest projected area over all cameras
+ * (tri_res_host uint32[F]), the corner that becomes the texture origin (faces_host int32[F][3] is REORDERED IN PLACE) and
+ * the first texel of each triangle (first_texel_host uint32[F]); *n_texels_host = getPrimitivesNum().
+ *   cameras: R_host float[n][9] row-major, t_host float[n][3], f_host / c_host double[n][2], resolution_host int32[n][2]
+ * Build the prepared mesh (smesh_raster_mesh_build) from the REORDERED faces, upload tri_res / first_texel, then
+ * smesh_raster_render_texels renders a view like smesh_raster_render, idx_out holding texel indices
+ * (TexturedTriangle::getTexelIndex, :32-41).
+ */
+int smesh_texels_prepare(const float* verts_host, int64_t V, int32_t* faces_host, int64_t F, int n_cameras, const float* R_host,
+                         const float* t_host, const double* f_host, const double* c_host, const int32_t* resolution_host,
+                         float texels_per_pixel, uint32_t* tri_res_host, uint32_t* first_texel_host, uint64_t* n_texels_host);
+int smesh_raster_render_texels(const void* mesh, size_t mesh_bytes, int64_t V, int64_t F, const uint32_t* tri_res,
+                               const uint32_t* first_texel, const float* R_host, const float* t_host, const double* f_host,
+                               const double* c_host, int W, int H, void* workspace, size_t workspace_bytes, uint32_t* idx_out,
+                               float* depth_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Label fusion: replaces ModelAggregator::{add1,add2,get,reset} (python/semantic_meshes/include/Fusion.h:42-76) ->
  * semantic_meshes::ModelAggregator::{add,get,reset} (include/semantic_meshes/fusion/Mesh.h:57-133) with the chains

@@ -24,6 +24,7 @@ def build(ref=False):
     if ref and os.path.isdir(os.environ.get("SMESH_REFERENCE", "/root/reference")):
         subprocess.run(["make", "-C", _HERE, "ref_fusion"], check=True, capture_output=True)
         subprocess.run(["make", "-C", _HERE, "ref_raster"], check=True, capture_output=True)
+        subprocess.run(["make", "-C", _HERE, "ref_texels"], check=True, capture_output=True)
 
 
 _lib = None
@@ -289,6 +290,127 @@ class RefRenderer:
     def close(self):
         if self._h:
             self._L.ref_raster_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# texel renderer (TexturedTriangleRenderer): restatement and genuine reference
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _camera_block(cameras):
+    """cameras: sequence of objects with rotation / translation / focal_lengths / principal_point / resolution (already
+    rounded like semantic_meshes.data.Camera does) -> flat arrays R [n,9], t [n,3], f [n,2], c [n,2], res [n,2]."""
+    n = len(cameras)
+    R = np.ascontiguousarray([_f32(c.rotation).reshape(9) for c in cameras], dtype=np.float32).reshape(n, 9)
+    t = np.ascontiguousarray([_f32(c.translation).reshape(3) for c in cameras], dtype=np.float32).reshape(n, 3)
+    f = np.ascontiguousarray([np.asarray(c.focal_lengths, dtype=np.float64).reshape(2) for c in cameras]).reshape(n, 2)
+    pp = np.ascontiguousarray([np.asarray(c.principal_point, dtype=np.float64).reshape(2) for c in cameras]).reshape(n, 2)
+    res = np.ascontiguousarray([np.asarray(c.resolution, dtype=np.int32).reshape(2) for c in cameras], dtype=np.int32).reshape(n, 2)
+    return R, t, f, pp, res
+
+
+def texels_prepare(verts, faces, cameras, texels_per_pixel=0.1):
+    """The constructor of TexturedTriangleRenderer -> (reordered faces int32 [F,3], tri_res uint32 [F],
+    first_texel uint32 [F], number of texels)."""
+    L = lib()
+    L.oracle_texels_prepare.restype = ctypes.c_uint64
+    L.oracle_texels_prepare.argtypes = [_c_void_p, _c_void_p, _i64, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                        _c_void_p, ctypes.c_float, _c_void_p, _c_void_p]
+    verts = _f32(verts).reshape(-1, 3)
+    faces = np.array(faces, dtype=np.int32, order="C", copy=True).reshape(-1, 3)
+    R, t, f, pp, res = _camera_block(cameras)
+    F = faces.shape[0]
+    tri_res = np.zeros(max(F, 1), dtype=np.uint32)
+    first = np.zeros(max(F, 1), dtype=np.uint32)
+    total = L.oracle_texels_prepare(verts.ctypes.data, faces.ctypes.data, F, len(cameras), R.ctypes.data, t.ctypes.data,
+                                    f.ctypes.data, pp.ctypes.data, res.ctypes.data, float(texels_per_pixel),
+                                    tri_res.ctypes.data, first.ctypes.data)
+    return faces, tri_res[:F], first[:F], int(total)
+
+
+def texels_render(verts, faces, tri_res, first_texel, R, t, f, c, W, H):
+    """TexturedTriangleRenderer::render with the REORDERED faces -> (texel idx uint32 [W,H], depth float32 [W,H])."""
+    L = lib()
+    L.oracle_texels_render.restype = _int
+    L.oracle_texels_render.argtypes = [_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                       _c_void_p, _int, _int, _c_void_p, _c_void_p]
+    verts = _f32(verts).reshape(-1, 3)
+    faces = np.ascontiguousarray(faces, dtype=np.int32).reshape(-1, 3)
+    tri_res = np.ascontiguousarray(tri_res, dtype=np.uint32)
+    first_texel = np.ascontiguousarray(first_texel, dtype=np.uint32)
+    R = _f32(R).reshape(9)
+    t = _f32(t).reshape(3)
+    f = np.ascontiguousarray(f, dtype=np.float64).reshape(2)
+    c = np.ascontiguousarray(c, dtype=np.float64).reshape(2)
+    idx = np.empty((W, H), dtype=np.uint32)
+    depth = np.empty((W, H), dtype=np.float32)
+    rc = L.oracle_texels_render(verts.ctypes.data, faces.ctypes.data, faces.shape[0], tri_res.ctypes.data,
+                                first_texel.ctypes.data, R.ctypes.data, t.ctypes.data, f.ctypes.data, c.ctypes.data, W, H,
+                                idx.ctypes.data, depth.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("oracle_texels_render failed")
+    return idx, depth
+
+
+def ref_texels_path():
+    return os.path.join(_HERE, "_ref", "libref_texels.so")
+
+
+class RefTexelRenderer:
+    """The genuine semantic_meshes::render::TexturedTriangleRenderer (host constructor + reference CUDA kernel; needs a
+    GPU) behind a C driver (oracle/ref_harness/ref_texels.cu)."""
+
+    def __init__(self, ply_path, cameras, texels_per_pixel=0.1):
+        L = ctypes.CDLL(ref_texels_path())
+        L.ref_texels_create.restype = _c_void_p
+        L.ref_texels_create.argtypes = [ctypes.c_char_p, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                        ctypes.c_float]
+        L.ref_texels_primitives.restype = ctypes.c_uint64
+        L.ref_texels_primitives.argtypes = [_c_void_p]
+        L.ref_texels_faces.restype = None
+        L.ref_texels_faces.argtypes = [_c_void_p, _c_void_p]
+        L.ref_texels_render.restype = _int
+        L.ref_texels_render.argtypes = [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _int, _int, _c_void_p, _c_void_p]
+        L.ref_texels_destroy.restype = None
+        L.ref_texels_destroy.argtypes = [_c_void_p]
+        L.ref_texels_last_error.restype = ctypes.c_char_p
+        self._L = L
+        R, t, f, pp, res = _camera_block(cameras)
+        self._h = L.ref_texels_create(str(ply_path).encode(), len(cameras), R.ctypes.data, t.ctypes.data, f.ctypes.data,
+                                      pp.ctypes.data, res.ctypes.data, float(texels_per_pixel))
+        if not self._h:
+            raise RuntimeError("ref_texels_create: " + L.ref_texels_last_error().decode())
+
+    def getPrimitivesNum(self):
+        return int(self._L.ref_texels_primitives(self._h))
+
+    def faces(self, F):
+        out = np.empty((F, 3), dtype=np.int32)
+        self._L.ref_texels_faces(self._h, out.ctypes.data)
+        return out
+
+    def render(self, R, t, f, c, W, H):
+        R = _f32(R).reshape(9)
+        t = _f32(t).reshape(3)
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(2)
+        c = np.ascontiguousarray(c, dtype=np.float64).reshape(2)
+        idx = np.empty((W, H), dtype=np.uint32)
+        depth = np.empty((W, H), dtype=np.float32)
+        rc = self._L.ref_texels_render(self._h, R.ctypes.data, t.ctypes.data, f.ctypes.data, c.ctypes.data, W, H,
+                                       idx.ctypes.data, depth.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("ref_texels_render: " + self._L.ref_texels_last_error().decode())
+        return idx, depth
+
+    def close(self):
+        if self._h:
+            self._L.ref_texels_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -23,6 +23,10 @@ SIGNATURES = {
     "smesh_raster_render": (_int, [_vp, _sz, _i64, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _vp, _vp, _vp]),
     "smesh_raster_render_counted": (_int, [_vp, _sz, _i64, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _vp, _vp, _vp, _u32,
                                            _vp]),
+    "smesh_texels_prepare": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp,
+                                    ctypes.POINTER(ctypes.c_uint64)]),
+    "smesh_raster_render_texels": (_int, [_vp, _sz, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _vp, _vp,
+                                          _vp]),
     "smesh_fuse_padded_classes": (_int, [_int]),
     "smesh_fuse_add": (_int, [_int, _vp, _int, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _int, _i64, _f32, _vp, _u32,
                               _vp, _vp, _vp]),

@@ -122,6 +122,72 @@ def triangles(ply, device=None):
     return TriangleRenderer(ply, device=device)
 
 
-def texels(*args, **kwargs):
-    raise NotImplementedError("render.texels (TexturedTriangleRenderer) is outside the B200 hot-path scope; "
-                              "use render.triangles")
+class TexturedTriangleRenderer(TriangleRenderer):
+    """render.texels(...): primitives are the texels of per-triangle textures
+    (include/semantic_meshes/render/TexturedTriangleRenderer.h). The constructor sizes every triangle's texture from its
+    largest projection over `cameras` and reorders each face's corners, on the host like the reference's; `render` is
+    the triangle rasterizer with the texel-index shader."""
+
+    def __init__(self, ply, cameras, texels_per_pixel=0.1, device=None):
+        torch = _lib.require_cuda()
+        if not isinstance(ply, Ply):
+            raise TypeError("render.texels expects a semantic_meshes.data.Ply")
+        cameras = list(cameras.getCameras()) if hasattr(cameras, "getCameras") else list(cameras)
+        for cam in cameras:
+            if not isinstance(cam, Camera):
+                raise TypeError("render.texels expects data.Camera objects or a data.Colmap workspace")
+        verts = np.ascontiguousarray(ply.vertices, dtype=np.float32)
+        faces = np.array(ply.faces, dtype=np.int32, order="C", copy=True)
+        F, n = faces.shape[0], len(cameras)
+        R = np.ascontiguousarray([c.rotation for c in cameras], dtype=np.float32).reshape(n, 9)
+        t = np.ascontiguousarray([c.translation for c in cameras], dtype=np.float32).reshape(n, 3)
+        f = np.ascontiguousarray([c.focal_lengths for c in cameras], dtype=np.float64).reshape(n, 2)
+        c = np.ascontiguousarray([c.principal_point for c in cameras], dtype=np.float64).reshape(n, 2)
+        res = np.ascontiguousarray([c.resolution for c in cameras], dtype=np.int32).reshape(n, 2)
+        tri_res = np.zeros(max(F, 1), dtype=np.uint32)
+        first = np.zeros(max(F, 1), dtype=np.uint32)
+        total = ctypes.c_uint64(0)
+        _lib.check(_lib.lib.smesh_texels_prepare(verts.ctypes.data, verts.shape[0], faces.ctypes.data, F, n, R.ctypes.data,
+                                                 t.ctypes.data, f.ctypes.data, c.ctypes.data, res.ctypes.data,
+                                                 float(texels_per_pixel), tri_res.ctypes.data, first.ctypes.data,
+                                                 ctypes.byref(total)))
+        self._texels = int(total.value)
+        self.faces = faces            # reordered like the reference reorders ply->getTinyplyFaces() (:133-150)
+        self.triangle_resolutions = tri_res[:F]
+        super().__init__(Ply.from_arrays(verts, faces), device=device)
+        self._tri_res = torch.from_numpy(tri_res.view(np.int32)).to(self.device)
+        self._first_texel = torch.from_numpy(first.view(np.int32)).to(self.device)
+
+    def getPrimitivesNum(self):
+        return self._texels
+
+    def render(self, camera, capsule=False):
+        """-> (texel_indices, depth), shapes (W, H); index 0xFFFFFFFF (-1) where nothing is hit."""
+        if not isinstance(camera, Camera):
+            raise TypeError("render expects a semantic_meshes.data.Camera")
+        torch = self._torch
+        W, H = camera.resolution
+        if W < 1 or H < 1:
+            raise ValueError("render: empty resolution")
+        with torch.cuda.device(self.device):
+            ws = self._ensure_workspace(W, H)
+            idx = torch.empty((W, H), dtype=torch.int32, device=self.device)
+            depth = torch.empty((W, H), dtype=torch.float32, device=self.device)
+            R, t = camera.rotation, camera.translation
+            f, c = camera.focal_lengths, camera.principal_point
+            rc = _lib.lib.smesh_raster_render_texels(self._mesh.data_ptr(), self._mesh.numel(), self._V, self._F,
+                                                     self._tri_res.data_ptr(), self._first_texel.data_ptr(), R.ctypes.data,
+                                                     t.ctypes.data, f.ctypes.data, c.ctypes.data, W, H, ws.data_ptr(),
+                                                     ws.numel(), idx.data_ptr(), depth.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc)
+        if capsule:
+            from torch.utils.dlpack import to_dlpack
+            return to_dlpack(idx.view(torch.uint32)), to_dlpack(depth)
+        return idx, depth
+
+
+def texels(ply, cameras, texels_per_pixel=0.1, device=None):
+    """render.texels(ply, colmap | [cameras][, texels_per_pixel]) (Render.cu:20-23,
+    python/semantic_meshes/include/Ply.h:54-119)."""
+    return TexturedTriangleRenderer(ply, cameras, texels_per_pixel, device=device)
