@@ -285,6 +285,27 @@ def test_full_size_configs_bit_exact(sm, name):
     assert gi[hit].max() < mesh.faces.shape[0] and np.isfinite(gd[hit]).all() and np.isinf(gd[~hit]).all()
 
 
+def test_degenerate_inputs(sm):
+    """An empty mesh, a single triangle, a 1x1 and a 1xN image, triangles with NaN / Inf corners and zero-area triangles:
+    whatever the reference's arithmetic makes of them (the oracle follows it), no crash."""
+    from semantic_meshes.data import Camera, Ply
+    cam = Camera(np.eye(3), np.zeros(3), np.array([40, 30]), np.array([35.0, 35.0]), np.array([20.0, 15.0]))
+    empty = Ply.from_arrays(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32))
+    idx, depth = sm.render.triangles(empty).render(cam)
+    assert (idx.cpu().numpy() == -1).all() and np.isinf(depth.cpu().numpy()).all()
+    verts = np.array([[-1, -1, 2], [1, -1, 2], [0, 1, 2],                 # a proper triangle
+                      [0, 0, 1], [0, 0, 1], [0, 0, 1],                    # zero area
+                      [np.nan, 0, 1], [1, 0, 1], [0, 1, 1],               # NaN corner
+                      [np.inf, 0, 3], [1, 0, 3], [0, 1, 3],               # Inf corner
+                      [-5, -5, 1.5], [5, -5, 1.5], [0, 5, -0.5]], dtype=np.float32)   # crosses the camera plane
+    mesh = Ply.from_arrays(verts, np.arange(15, dtype=np.int32).reshape(5, 3))
+    renderer = sm.render.triangles(mesh)
+    for res in ((40, 30), (1, 1), (1, 17), (23, 1)):
+        c = Camera(np.eye(3), np.zeros(3), np.array(res), np.array([35.0, 35.0]), np.array([res[0] / 2, res[1] / 2]))
+        gi, gd, oi, od = render_both(sm, mesh, c, renderer)
+        assert_bit_exact(gi, gd, oi, od)
+
+
 def test_intrinsics_change_rebuilds_ray_table(sm):
     """The per-pixel ray normalisation is cached per intrinsics inside the renderer's workspace."""
     from semantic_meshes import synthetic
