@@ -409,11 +409,13 @@ def test_add_batch_equals_sequential(sm):
     assert_acc_close("sum", b.state().cpu().numpy(), ref.acc)
 
 
-def test_full_size_properties(sm):
-    """Config 3 shape (2 M primitives, 2048x1024x19): too big for the oracle in seconds, so check size-independent
-    properties against a plain torch fp32 statement of the same op (bincount + index_add_), plus linearity."""
+@pytest.mark.parametrize("shape", [(2048, 1024, 19, 2_000_000), (640, 480, 40, 500_000), (1920, 1080, 150, 1_000_000)])
+def test_full_size_properties(sm, shape):
+    """Configs 3, 2 and 4 at full size (e.g. 2 M primitives, 2048x1024x19; 1920x1080x150 = 1.2 GB of predictions): too big
+    for the oracle in seconds, so check size-independent properties against a plain torch fp32 statement of the same op
+    (bincount + index_add_), plus linearity."""
     import torch
-    W, H, C, P = 2048, 1024, 19, 2_000_000
+    W, H, C, P = shape
     g = torch.Generator(device="cuda").manual_seed(5)
     # 4x4-pixel blocks of random faces, 10 % background
     base = torch.randint(0, P, (W // 4, H // 4), generator=g, device="cuda", dtype=torch.int32)
