@@ -7,8 +7,8 @@ One STEP = one pass over a batch of B synthetic views: for every view, render th
 + depth image) and fuse that view's (W, H, C) prediction into the per-face accumulator. `value` = views/s over all ranks
 with every input already resident in HBM (the step is replayed as a CUDA graph); `e2e` = the same loop through the
 public Python API with the predictions in pinned HOST memory (H2D copy of every view and a D2H read of the last view's
-render result inside the timed region). `roofline` is the scatter kernel of MeshAggregator.add (the dominant kernel)
-against the measured HBM peak; `cpu_baseline` / `--impl reference` time the GENUINE reference (oracle/_ref, compiled from
+render result inside the timed region). `roofline` is the scatter kernel of MeshAggregator.add (the dominant kernel
+of the HBM-bound path; timed as the B views' launches back to back in a CUDA graph) against the measured HBM peak; `cpu_baseline` / `--impl reference` time the GENUINE reference (oracle/_ref, compiled from
 the reference's sources) on the host cores of the same box.
 
 Multi-GPU (torchrun, one rank per GPU): views shard across ranks (weak scaling: every rank runs the same number of
