@@ -1,7 +1,7 @@
 """Diagnostic (GPU box): genuine reference kernel vs oracle on the scenes of test_against_genuine_reference_kernel."""
 import os, sys, tempfile
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "semantic-meshes_b200"), os.path.join(ROOT, "tests")]
 import oracle
 from conftest import write_plain_ply
