@@ -56,6 +56,8 @@ class MeshAggregator:
         self._ids32 = torch.empty((0,), dtype=torch.int32, device=self.device)
         self._epoch = 0      # last count epoch handed out (see include/smesh.h: tagged per-view pixel counters)
         self._epoch_gen = 0  # bumped whenever the counters are zeroed: tokens of earlier counted renders become void
+        # upload path of host predictions (see _upload_probs)
+        self._copy_stream, self._stage_bufs, self._stage_done, self._stage_next, self._stage_last = None, [None, None], [None, None], 0, None
 
     # ---------------------------------------------------------------------------------------------------------------
     def _as_tensor(self, obj, what):
@@ -73,8 +75,44 @@ class MeshAggregator:
         else:
             raise ValueError(_NONE_MATCHED + f"{what} has type {type(obj).__name__}")
         if t.device != self.device:
+            if what == "probs" and t.device.type == "cpu" and t.is_contiguous() and not torch.cuda.is_current_stream_capturing():
+                return self._upload_probs(t)
             t = t.to(self.device, non_blocking=True)
         return t
+
+    def _upload_probs(self, host):
+        """Host predictions (159 MB per view at config 3) go up on a copy stream into one of two staging buffers, so the
+        upload of view v+1 overlaps the kernels of view v; the compute stream waits for its view's upload, the copy stream
+        for the kernels that last read the buffer it is about to overwrite (`_stage_done`, set at the end of add)."""
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream()
+            k = self._stage_next
+            self._stage_next ^= 1
+            buf = self._stage_bufs[k]
+            if buf is None or buf.shape != host.shape or buf.dtype != host.dtype:
+                buf = self._stage_bufs[k] = torch.empty(host.shape, dtype=host.dtype, device=self.device)
+                self._stage_done[k] = None
+            cs, main = self._copy_stream, torch.cuda.current_stream()
+            cs.wait_stream(main) if self._stage_done[k] is None else cs.wait_event(self._stage_done[k])
+            with torch.cuda.stream(cs):
+                buf.copy_(host, non_blocking=True)
+                up = torch.cuda.Event()
+                up.record(cs)
+            main.wait_event(up)
+            self._stage_last = k
+        return buf
+
+    def _release_stage(self):
+        """Called after the kernels of an add have been enqueued: the staging buffer they read may be overwritten once
+        they are done."""
+        k = self._stage_last
+        if k is not None:
+            ev = self._torch.cuda.Event()
+            ev.record(self._torch.cuda.current_stream())
+            self._stage_done[k] = ev
+            self._stage_last = None
 
     def _stage(self, primitive_indices, probs, weights):
         """Validate like Fusion.h:42-64 / Mesh.h:68-74 and move to the device. -> (ids, id_dtype, probs, weights)"""
@@ -186,6 +224,7 @@ class MeshAggregator:
                                                  wt.data_ptr() if wt is not None else None, n_outer * n_inner, self.classes,
                                                  self.primitives, self.images_equal_weight,
                                                  self._counts_for(epoch).data_ptr(), epoch, self._acc.data_ptr(), stream)
+            self._release_stage()
             _lib.check(rc)
             return
         epoch = self._next_epochs(n_outer * n_inner)
@@ -195,6 +234,7 @@ class MeshAggregator:
                                          self.classes, self.primitives, self.images_equal_weight,
                                          self._counts_for(epoch).data_ptr(), epoch,
                                          self._scratch(n_outer * n_inner).data_ptr(), self._acc.data_ptr(), stream)
+        self._release_stage()
         _lib.check(rc)
 
     def add_batch(self, primitive_indices, probs, weights=None):
@@ -233,6 +273,7 @@ class MeshAggregator:
                     torch.cuda.current_stream().cuda_stream)
             _lib.check(rc)
             done += nb
+        self._release_stage()
 
     def reset(self):
         """ModelAggregator::reset (Mesh.h:119-122): every row back to the aggregator's zero (mul: -log 1 = 0)."""

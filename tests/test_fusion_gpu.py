@@ -369,6 +369,32 @@ def test_labels_colors_and_gather_back(sm):
     assert np.array_equal(img64, exp)
 
 
+def test_host_predictions_upload_overlapped(sm):
+    """Predictions handed to add() in HOST memory (pinned torch tensors, plain numpy arrays, a transposed host view) are
+    uploaded on a copy stream into two alternating staging buffers while the previous view is still being fused: many
+    views in a row, mixed with device inputs and changing shapes, must give what the device path gives."""
+    import torch
+    C, P = 19, 500
+    rng = np.random.default_rng(77)
+    dev_agg, host_agg = sm.fusion.MeshAggregator(P, C), sm.fusion.MeshAggregator(P, C)
+    for v in range(9):
+        W, H = (96, 80) if v % 4 != 3 else (64, 72)          # a shape change reallocates the staging buffer
+        ids, probs = make_view(rng, W, H, C, P, block=3)
+        ids_d = torch.from_numpy(ids.view(np.int32)).cuda()
+        dev_agg.add(ids_d, torch.from_numpy(probs).cuda())
+        if v % 3 == 0:
+            host = torch.from_numpy(probs).pin_memory()
+        elif v % 3 == 1:
+            host = probs                                      # numpy, pageable
+        else:
+            host = torch.from_numpy(np.ascontiguousarray(probs.transpose(1, 0, 2))).pin_memory().permute(1, 0, 2)
+        host_agg.add(ids_d if v % 2 else ids.view(np.int32), host)
+        if v == 4:
+            host_agg.add(ids_d, torch.from_numpy(probs).cuda())   # a device input in between
+            dev_agg.add(ids_d, torch.from_numpy(probs).cuda())
+    torch.testing.assert_close(host_agg.state(), dev_agg.state(), rtol=1e-6, atol=1e-7)
+
+
 def test_count_epoch_wraparound(sm):
     """The per-view pixel counters are tagged with an 8-bit epoch instead of being cleared (include/smesh.h); 600 views
     cross the wrap twice, and the face -> pixel-count mapping changes every view."""
