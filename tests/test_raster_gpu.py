@@ -306,7 +306,7 @@ def test_degenerate_inputs(sm):
         assert_bit_exact(gi, gd, oi, od)
 
 
-@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("SMESH_FUZZ_SEEDS", "6"))))
 def test_fuzz_random_scenes(sm, seed):
     """Random meshes (terrain patches, icospheres, triangle soups), random poses - above, inside, beside, looking away -
     random intrinsics (focal 30 ... 3000 px, principal point anywhere in or near the image) and resolutions: eight views per
