@@ -45,3 +45,33 @@ def test_constructor_matches_oracle_and_definition():
             return np.abs(np.arccos(np.clip(cosv, -1, 1)) - np.pi / 2)
         d = np.stack([ang(of, j) for j in range(3)], 1)
         assert (d[:, 0] <= d[:, 1] + 1e-5).all() and (d[:, 0] <= d[:, 2] + 1e-5).all() and (d[:, 1] <= d[:, 2] + 1e-5).all()
+
+
+def test_texel_shader_against_its_definition():
+    """TexturedTriangle::getTexelIndex (TexturedTriangleRenderer.h:32-41) on one fronto-parallel right triangle with a
+    resolution of 8: for every pixel safely inside a texel, the oracle's index must be the lower-triangular index of
+    trunc(uv * 8) computed here in double from the pixel's barycentric coordinates."""
+    import oracle
+    from semantic_meshes.data import Camera
+    # corner 0 at the right angle: u runs along edge 0->1, v along edge 0->2 (uv = bc1 * (1,0) + bc2 * (0,1))
+    verts = np.array([[-1.0, -1.0, 2.0], [1.0, -1.0, 2.0], [-1.0, 1.0, 2.0]], dtype=np.float32)
+    faces = np.array([[0, 1, 2]], dtype=np.int32)
+    W = H = 240
+    f, c = 100.0, 120.0
+    cam = Camera(np.eye(3), np.zeros(3), np.array([W, H]), np.array([f, f]), np.array([c, c]))
+    res, first = np.array([8], dtype=np.uint32), np.array([5], dtype=np.uint32)
+    idx, depth = oracle.texels_render(verts, faces, res, first, cam.rotation, cam.translation, cam.focal_lengths,
+                                      cam.principal_point, W, H)
+    xs, ys = np.meshgrid(np.arange(W), np.arange(H), indexing="ij")
+    # pixel (x, y) sees the plane z = 2 at ((x - c) / f * 2, (y - c) / f * 2): u = (X + 1) / 2, v = (Y + 1) / 2
+    u = ((xs - c) / f * 2 + 1) / 2
+    v = ((ys - c) / f * 2 + 1) / 2
+    inside = (u > 0.01) & (v > 0.01) & (u + v < 0.99)
+    safe = inside & (np.abs(u * 8 - np.round(u * 8)) > 0.02) & (np.abs(v * 8 - np.round(v * 8)) > 0.02)
+    row, col = np.floor(u * 8).astype(np.int64), np.floor(v * 8).astype(np.int64)
+    expect = 5 + np.where(row >= col, (row + 1) * row // 2 + col, (col + 1) * col // 2 + row)
+    assert safe.sum() > 3000
+    assert np.array_equal(idx[safe].astype(np.int64), expect[safe])
+    assert (idx[inside] != 0xFFFFFFFF).all() and np.allclose(depth[inside], 2.0, rtol=1e-6)
+    hit = idx != 0xFFFFFFFF
+    assert set(np.unique(idx[hit]) - 5) <= set(range(8 * 9 // 2 + 8))      # inside the triangle's texel range (+ diagonal)
