@@ -207,7 +207,11 @@ class MeshAggregator:
     def add(self, primitive_indices, probs, weights=None):
         """Fuse one view (ModelAggregator::add, Mesh.h:65-107). If `primitive_indices` comes from
         `renderer.render(camera, count_into=self)` the per-face pixel counts are already in place and only the scatter
-        stage runs."""
+        stage runs.
+
+        The call is asynchronous on the current CUDA stream (the reference's is synchronous). Inputs in pageable host memory
+        (numpy arrays) have been read when it returns; a PINNED host tensor is read by an asynchronous copy, like
+        `tensor.to(device, non_blocking=True)`: do not overwrite it before the stream has caught up."""
         torch = self._torch
         ids, id_dtype, pr, wt = self._stage(primitive_indices, probs, weights)
         lay = self._layout(ids, pr, wt)
