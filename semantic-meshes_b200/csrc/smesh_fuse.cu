@@ -13,7 +13,7 @@
 //                       sum, Mesh.h:98) and weight (Mesh.h:100-103), then lanes regroup as (run of equal face id, 4-class
 //                       chunk) to reduce the run in registers and issue ONE 128-bit red.global.add.v4.f32 per chunk into
 //                       the 16-byte padded accumulator row
-//                       (C = 19: scatter_pair_kernel, two pixels per lane; wide C: scatter_rows_kernel, lanes across the
+//                       (C = 2 ... 20: scatter_pair_kernel, two pixels per lane; wide C: scatter_rows_kernel, lanes across the
 //                       classes of a pixel, rows read straight from global memory)
 //   3. clear_kernel   - only in the untagged-counter mode (images of >= 2^24 pixels): zero the touched counters again
 // No tensor cores: this is an irregular gather/scatter, not a contraction.
@@ -21,6 +21,8 @@
 
 #include <math_constants.h>
 #include <stdlib.h>
+
+#include <algorithm>
 
 namespace smesh {
 namespace fuse {
@@ -540,7 +542,7 @@ __global__ void __launch_bounds__(288) scatter_kernel(ScatterArgs a)
 template <int KIND, int CT>
 __global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
 {
-  static_assert(CT >= 1 && CT <= CH, "pair kernel holds 2 x CT values in registers");
+  static_assert(CT >= 1 && CT <= CH, "pair kernel holds 2 x Cpad values in registers");
   constexpr int C = CT;
   constexpr int Cpad = (CT + 3) & ~3;
   constexpr int NCHUNK = Cpad / 4;
@@ -665,9 +667,9 @@ __global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
       ab[2 * k] = t.x;
       ab[2 * k + 1] = t.y;
     }
-    float A[CH], B[CH];
+    float A[Cpad], B[Cpad];
 #pragma unroll
-    for (int k = 0; k < CH; k++)
+    for (int k = 0; k < Cpad; k++)
     {
       A[k] = k < C ? ab[k] : 0.0f;
       B[k] = k < C ? ab[C + k] : 0.0f;
@@ -685,7 +687,7 @@ __global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
     const float wA = pixel_weight(a.iew, n.x & a.count_mask, wt.x);
     const float wB = pixel_weight(a.iew, n.y & a.count_mask, wt.y);
 #pragma unroll
-    for (int k = 0; k < CH; k++)
+    for (int k = 0; k < Cpad; k++)
     {
       if (KIND == SMESH_KIND_SUM)
       {
@@ -706,7 +708,7 @@ __global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
     if (merged)
     {
 #pragma unroll
-      for (int k = 0; k < CH; k++)
+      for (int k = 0; k < Cpad; k++)
       {
         A[k] = __fadd_rn(A[k], B[k]); // S = A + B
       }
@@ -729,7 +731,7 @@ __global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
     {
       const bool take = lane + d < end;
 #pragma unroll
-      for (int k = 0; k < CH; k++)
+      for (int k = 0; k < Cpad; k++)
       {
         const float t = __shfl_down_sync(0xFFFFFFFFu, A[k], d);
         if (take)
@@ -742,7 +744,7 @@ __global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
     if (__any_sync(0xFFFFFFFFu, contT))
     {
 #pragma unroll
-      for (int k = 0; k < CH; k++)
+      for (int k = 0; k < Cpad; k++)
       {
         const float t = __shfl_down_sync(0xFFFFFFFFu, A[k], 1);
         if (contT)
@@ -1265,11 +1267,14 @@ struct PairConfig
   int stages;
 };
 
-static PairConfig pair_config()
+static PairConfig pair_config(int C)
 {
   // 3 consumer warps x 2 stages = 45.5 KB per CTA, four CTAs per SM: the same speed alone as 4 warps x 3 CTAs, and 7 % more
-  // views/s when the rasterizer shares the SMs (finer-grained CTAs interleave better), measured on cfg3
+  // views/s when the rasterizer shares the SMs (finer-grained CTAs interleave better), measured on cfg3 (C = 19).
+  // Narrower class vectors get more stages so that a CTA keeps about the same 28 KB of bulk copies in flight.
   PairConfig cfg = {3, 2};
+  const int stage_bytes = cfg.consumer_warps * 64 * C * 4;
+  cfg.stages = std::min(8, std::max(2, (28 * 1024 + stage_bytes - 1) / stage_bytes));
   static const int env_nw = getenv("SMESH_PAIR_NW") ? atoi(getenv("SMESH_PAIR_NW")) : 0;
   static const int env_stages = getenv("SMESH_PAIR_STAGES") ? atoi(getenv("SMESH_PAIR_STAGES")) : 0;
   if (env_nw >= 1 && env_nw <= 8) cfg.consumer_warps = env_nw;
@@ -1281,7 +1286,7 @@ template <int KIND, int CT>
 static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
 {
   ScatterArgs args = args_in;
-  const PairConfig cfg = pair_config();
+  const PairConfig cfg = pair_config(CT);
   const size_t smem = (size_t) cfg.stages * cfg.consumer_warps * 64 * CT * 4 + (size_t) cfg.stages * 16 +
                       (size_t) cfg.consumer_warps * (64 * ((CT + 3) & ~3) + 64) * 4; // flush rows + their face ids
   auto kernel = scatter_pair_kernel<KIND, CT>;
@@ -1337,14 +1342,16 @@ static int launch_scatter(const ScatterArgs& args, cudaStream_t stream)
   {
     if (KIND != SMESH_KIND_SUMMAX && !no_pair && (reinterpret_cast<uintptr_t>(args.ids) & 7) == 0)
     {
-      // narrow class vectors: two pixels per lane
+      // narrow class vectors (2 ... CH classes): two pixels per lane
+      constexpr int K = KIND == SMESH_KIND_SUMMAX ? SMESH_KIND_SUM : KIND;
       switch (args.C)
       {
-        case 19:
-        {
-          constexpr int K = KIND == SMESH_KIND_SUMMAX ? SMESH_KIND_SUM : KIND;
-          return launch_scatter_pair<K, 19>(args, stream);
-        }
+#define SMESH_PAIR_CASE(c) case c: return launch_scatter_pair<K, c>(args, stream);
+        SMESH_PAIR_CASE(2) SMESH_PAIR_CASE(3) SMESH_PAIR_CASE(4) SMESH_PAIR_CASE(5) SMESH_PAIR_CASE(6)
+        SMESH_PAIR_CASE(7) SMESH_PAIR_CASE(8) SMESH_PAIR_CASE(9) SMESH_PAIR_CASE(10) SMESH_PAIR_CASE(11)
+        SMESH_PAIR_CASE(12) SMESH_PAIR_CASE(13) SMESH_PAIR_CASE(14) SMESH_PAIR_CASE(15) SMESH_PAIR_CASE(16)
+        SMESH_PAIR_CASE(17) SMESH_PAIR_CASE(18) SMESH_PAIR_CASE(19) SMESH_PAIR_CASE(20)
+#undef SMESH_PAIR_CASE
         default: break;
       }
     }

@@ -249,6 +249,33 @@ def test_pair_kernel_shapes(sm, kind, shape):
 
 
 @pytest.mark.parametrize("kind", ["sum", "mul"])
+@pytest.mark.parametrize("C", [2, 3, 4, 5, 7, 8, 12, 13, 16, 17, 18, 20, 21])
+def test_narrow_class_vectors(sm, kind, C):
+    """Every class count from 2 to 20 has its own instance of the two-pixels-per-lane kernel (odd and even C, one to five
+    128-bit chunks per accumulator row, 2 to 8 ring stages); 21 is the first count that takes the per-pixel ring kernel.
+    Ragged image (tiles end inside a column), faces of 1 to 36 pixels, weights, gate edge cases."""
+    import torch
+    W, H, P = 53, 131, 250
+    rng = np.random.default_rng(C * 31 + len(kind))
+    agg = sm.fusion.MeshAggregator(primitives=P, classes=C, aggregator=kind)
+    ref = oracle.Aggregator(P, C, kind)
+    for v in range(3):
+        ids, probs = make_view(rng, W, H, C, P, block=(1, 2, 6)[v])
+        flat = probs.reshape(-1, C)
+        pick = rng.choice(flat.shape[0], flat.shape[0] // 10, replace=False)
+        for k, i in enumerate(pick):
+            row = np.abs(rng.normal(size=C)).astype(np.float32) + np.float32(1e-3)
+            scale = (0.5, 0.5 * (1 - 3e-4), 0.5 * (1 + 3e-4))[k % 3]            # at, just below, just above the gate
+            flat[i] = row * (np.float32(scale) / row.sum(dtype=np.float32))
+        wts = (rng.random((W, H)) * 2).astype(np.float32) if v == 1 else None
+        agg.add(torch.from_numpy(ids.view(np.int32)).cuda(), torch.from_numpy(probs).cuda(),
+                None if wts is None else torch.from_numpy(wts).cuda())
+        ref.add(ids, probs, wts)
+    assert_acc_close(kind, agg.state().cpu().numpy(), ref.acc)
+    assert_get_close(kind, agg.get(), ref.get())
+
+
+@pytest.mark.parametrize("kind", ["sum", "mul"])
 @pytest.mark.parametrize("shape", [(40, 64), (23, 128), (50, 260), (17, 1080), (300, 256), (7, 2048), (64, 516)])
 def test_tall_column_shapes(sm, kind, shape):
     """C = 19 images with tall columns (64 ... 2048 pixels, not always a multiple of the 256-pixel tile): faces from 1 pixel
