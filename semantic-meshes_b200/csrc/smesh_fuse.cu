@@ -539,8 +539,10 @@ __global__ void __launch_bounds__(288) scatter_kernel(ScatterArgs a)
 // finished chain of its right neighbour to T. Run heads (S or T) issue the 128-bit reductions.
 // ---------------------------------------------------------------------------------------------------------------------
 
-template <int KIND, int CT>
-__global__ void __launch_bounds__(288) scatter_pair_kernel(ScatterArgs a)
+// LEAN: compiled for 8 CTAs of <= 3 consumer warps per SM (64 registers instead of 84, 24 bytes of spills): leaves room
+// for more rasterizer CTAs next to it. Opt-in (SMESH_PAIR_LEAN=1, C = 19), not measured yet.
+template <int KIND, int CT, bool LEAN = false>
+__global__ void __launch_bounds__(LEAN ? 128 : 288, LEAN ? 8 : 0) scatter_pair_kernel(ScatterArgs a)
 {
   static_assert(CT >= 1 && CT <= CH, "pair kernel holds 2 x Cpad values in registers");
   constexpr int C = CT;
@@ -1282,14 +1284,22 @@ static PairConfig pair_config(int C)
   return cfg;
 }
 
-template <int KIND, int CT>
+template <int KIND, int CT, bool LEAN = false>
 static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
 {
   ScatterArgs args = args_in;
   const PairConfig cfg = pair_config(CT);
+  if (CT == 19 && !LEAN && cfg.consumer_warps <= 3)
+  {
+    static const bool lean = getenv("SMESH_PAIR_LEAN") != nullptr && atoi(getenv("SMESH_PAIR_LEAN")) != 0;
+    if (lean)
+    {
+      return launch_scatter_pair<KIND, CT == 19 ? 19 : 2, CT == 19>(args_in, stream);
+    }
+  }
   const size_t smem = (size_t) cfg.stages * cfg.consumer_warps * 64 * CT * 4 + (size_t) cfg.stages * 16 +
                       (size_t) cfg.consumer_warps * (64 * ((CT + 3) & ~3) + 64) * 4; // flush rows + their face ids
-  auto kernel = scatter_pair_kernel<KIND, CT>;
+  auto kernel = scatter_pair_kernel<KIND, CT, LEAN>;
   static thread_local size_t configured_smem = 0;
   static thread_local int blocks_per_sm = 0;
   static thread_local int configured_threads = 0;
