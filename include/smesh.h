@@ -9,7 +9,8 @@
  * Conventions
  *   - plain C types only; every pointer is a DEVICE pointer unless its name ends in _host;
  *   - the caller owns every buffer (the Python layer holds them as torch tensors); the library keeps no state between
- *     calls except the per-thread error string, so it is safe to use from several host threads / streams;
+ *     calls except the per-thread error string, per-kernel launch configuration and the side stream of
+ *     smesh_fuse_add_batch, so it is safe to use from several host threads / streams;
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and never synchronises the device;
  *   - return value 0 = success; anything else is an smesh_status and smesh_last_error() describes it
  *     (SMESH_ERR_INVALID_ARGUMENT maps to the reference's std::invalid_argument -> Python ValueError);
@@ -194,12 +195,17 @@ int smesh_fuse_clear(const uint32_t* ids32, int64_t n_pix, int64_t P, uint32_t* 
  * A batch of B views with identical shapes, view b at ids + b*ids_stride_view (elements), probs + b*probs_stride_view
  * (floats), weights + b*w_stride_view (floats, if weights != NULL). Equivalent to B calls of smesh_fuse_add in order with
  * epochs count_epoch0, count_epoch0 + 1, ... (all <= 255), or all 0.
+ *   counts2  uint32[2][P]: TWO counter arrays; the view with epoch e counts into array e & 1 (epoch 0: array 0 only).
+ *            With tagged epochs and 32-bit flat ids the count stage of view b+1 runs on an internal side stream (one
+ *            per host thread and device, created on first use) under the scatter stage of view b; the side stream has
+ *            joined `stream` again when the call returns, so the call is still stream-ordered for the caller and may
+ *            be captured into a CUDA graph.
  */
 int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id_dtype, int64_t ids_stride_view,
                          int64_t ids_stride_outer, int64_t ids_stride_inner, const float* probs,
                          int64_t probs_stride_view, const float* weights, int64_t w_stride_view, int64_t w_stride_outer,
                          int64_t w_stride_inner, int64_t n_outer, int64_t n_inner, int C, int64_t P, float iew,
-                         uint32_t* counts, uint32_t count_epoch0, uint32_t* ids32, float* acc, void* stream);
+                         uint32_t* counts2, uint32_t count_epoch0, uint32_t* ids32, float* acc, void* stream);
 
 /*
  * ModelAggregator::get (Fusion.h:72-76): out float32[P][C] = per-face class distribution: the accumulator row

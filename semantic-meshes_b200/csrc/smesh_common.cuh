@@ -13,6 +13,9 @@ namespace smesh {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t err, const char* what);
 int num_sms();
+// Opts `fn` in to `smem` bytes of dynamic shared memory on the current device (raise-only, thread-safe) and reports how
+// many CTAs of `threads` threads with that much shared memory fit on an SM.
+int kernel_blocks_per_sm(const void* fn, int threads, size_t smem, int* blocks_per_sm);
 
 #define SMESH_CUDA_CHECK(expr)                                  \
   do                                                            \

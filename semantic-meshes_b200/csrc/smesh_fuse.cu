@@ -59,12 +59,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     "{\n"
     ".reg .pred p;\n"
     "SMESH_WAIT_%=:\n"
-    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
     "@p bra SMESH_DONE_%=;\n"
     "bra SMESH_WAIT_%=;\n"
     "SMESH_DONE_%=:\n"
     "}\n" ::"r"(smem_u32(bar)),
-    "r"(parity)
+    "r"(parity), "r"(0x989680u) // suspend-time hint: the thread sleeps in hardware until the phase completes instead of
+                                // coming back to poll (the polling of 592 producers was 5 M warp instructions per view)
     : "memory");
 }
 
@@ -109,8 +110,21 @@ __device__ __forceinline__ float pixel_weight(float iew, uint32_t n, float wt)
 
 // mul aggregator input: LogProb(pow(p, w)) as -log (Fusion.cu:83-87, tt/numeric/LogProb.h:66-71); "zero" (isinf of
 // either sign) is the absorbing +inf (LogProb.h:106-118).
-__device__ __forceinline__ float neg_log_pow(float p, float w)
+// The reference's powf + logf pair costs ~150 instructions per class. -log(p^w) = -w log p, and as long as q = p^w stays a
+// normal float (|w log p| < 80, p > 0, w > 0) the reference's value is -log(fl(q)) = -w log p within 6e-8 absolute (the
+// rounding of q, which the direct form does not even have) + 2e-7 relative (logf): the direct form is used there. Anything
+// else - underflow of q to the absorbing zero, overflow, p <= 0, NaN, w <= 0 - takes the reference's own sequence.
+// `exact` (SMESH_MUL_EXACT=1, verification) forces that sequence everywhere.
+__device__ __forceinline__ float neg_log_pow(float p, float w, bool exact)
 {
+  if (!exact)
+  {
+    const float l = __fmul_rn(-w, logf(p));
+    if (p > 0.0f && w > 0.0f && fabsf(l) < 80.0f)
+    {
+      return l;
+    }
+  }
   const float q = powf(p, w);
   float l = (q == 0.0f) ? CUDART_INF_F : -logf(q);
   if (isinf(l))
@@ -150,57 +164,98 @@ __device__ __forceinline__ uint32_t sanitize_id(int64_t raw, int64_t P)
   return (raw >= 0 && raw < P) ? (uint32_t) raw : INVALID_ID;
 }
 
-constexpr int COUNT_UNROLL = 4; // independent 32-pixel groups per warp iteration (loads in flight per lane)
+// A warp counts a BLOCK of the image: COUNT_COLS consecutive outer indices (image columns) x 32 consecutive inner ones
+// (rows), lane = row. Inside a column, runs of equal ids are found by ballot (one length per run head). A face covers a
+// few adjacent columns at overlapping rows, so the run of a face in column k+1 is then folded into its run in column k
+// (right to left, lengths travel by shuffle): one pair of reductions per face and block instead of one per face and
+// column - the kernel is bound by the issue rate of scattered global reductions (~1.3 cycles per lane and SM).
+constexpr int COUNT_COLS = 8;
 
 template <typename IdT>
 __global__ void __launch_bounds__(256) count_kernel(const IdT* __restrict__ ids, int64_t stride_outer, int64_t stride_inner,
-                                                    int64_t n_inner, int64_t npix, int64_t P, uint32_t* __restrict__ counts,
-                                                    uint32_t* __restrict__ ids32, int flat, uint32_t epoch)
+                                                    int64_t n_outer, int64_t n_inner, int64_t P, uint32_t* __restrict__ counts,
+                                                    uint32_t* __restrict__ ids32, uint32_t epoch)
 {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
   const uint32_t tag = epoch << COUNT_BITS;
-  for (int64_t base = warp_global * (32 * COUNT_UNROLL); base < npix; base += nwarps * (32 * COUNT_UNROLL))
+  const int64_t nib = (n_inner + 31) >> 5;                                 // blocks along the inner axis
+  const int64_t nblocks = nib * ((n_outer + COUNT_COLS - 1) / COUNT_COLS);
+  const uint32_t ge_lane = ~((1u << lane) - 1u);                           // lanes >= this one
+  for (int64_t blk = warp_global; blk < nblocks; blk += nwarps)
   {
-    uint32_t id[COUNT_UNROLL];
+    const int64_t ob = blk / nib, ib = blk - ob * nib;
+    const int64_t in = ib * 32 + lane;
+    uint32_t id[COUNT_COLS];
 #pragma unroll
-    for (int k = 0; k < COUNT_UNROLL; k++)
+    for (int k = 0; k < COUNT_COLS; k++)
     {
-      const int64_t i = base + k * 32 + lane;
+      const int64_t o = ob * COUNT_COLS + k;
       id[k] = INVALID_ID;
-      if (i < npix)
+      if (o < n_outer && in < n_inner)
       {
-        int64_t off = i;
-        if (!flat)
+        id[k] = sanitize_id(ids[o * stride_outer + in * stride_inner], P);
+        if (ids32 != nullptr)
         {
-          const int64_t o = i / n_inner, in = i - o * n_inner;
-          off = o * stride_outer + in * stride_inner;
+          ids32[o * n_inner + in] = id[k];
         }
-        id[k] = sanitize_id(ids[off], P);
+      }
+    }
+    // runs inside each column: head lanes hold the run length
+    uint32_t len[COUNT_COLS], headmask[COUNT_COLS];
+#pragma unroll
+    for (int k = 0; k < COUNT_COLS; k++)
+    {
+      const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, id[k], 1);
+      const bool head = (lane == 0) || (prev != id[k]);
+      headmask[k] = __ballot_sync(0xFFFFFFFFu, head);
+      const uint32_t above = headmask[k] & ~((2u << lane) - 1u);
+      const int next = above ? (__ffs(above) - 1) : 32;
+      len[k] = (head && id[k] != INVALID_ID) ? (uint32_t) (next - lane) : 0u;
+    }
+    // fold column k+1 into column k: a run of column k takes over the (already folded) run of column k+1 that shares a
+    // row and the id with it. Several runs of column k may point at the same run of column k+1 (a face split by an
+    // occluder): only the lowest lane of such a group takes it.
+#pragma unroll
+    for (int k = COUNT_COLS - 2; k >= 0; k--)
+    {
+      const uint32_t eq = __ballot_sync(0xFFFFFFFFu, id[k] == id[k + 1] && id[k] != INVALID_ID);
+      int want = -1;
+      if (len[k] != 0u)
+      {
+        const uint32_t above = headmask[k] & ~((2u << lane) - 1u);
+        const uint32_t range = ge_lane & (above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xFFFFFFFFu); // rows of this run
+        const uint32_t m = eq & range;
+        if (m != 0u)
+        {
+          const int r = __ffs(m) - 1;
+          want = 31 - __clz(headmask[k + 1] & ((2u << r) - 1u)); // head of the run of column k+1 that holds row r
+        }
+      }
+      const uint32_t same = __match_any_sync(0xFFFFFFFFu, want);
+      const bool take = want >= 0 && (same & ((1u << lane) - 1u)) == 0u;
+      const uint32_t moved = __shfl_sync(0xFFFFFFFFu, len[k + 1], want >= 0 ? want : 0);
+      const uint32_t consumed = __reduce_or_sync(0xFFFFFFFFu, take ? (1u << want) : 0u);
+      if (take)
+      {
+        len[k] += moved;
+      }
+      if ((consumed >> lane) & 1u)
+      {
+        len[k + 1] = 0u;
       }
     }
 #pragma unroll
-    for (int k = 0; k < COUNT_UNROLL; k++)
+    for (int k = 0; k < COUNT_COLS; k++)
     {
-      const int64_t i = base + k * 32 + lane;
-      if (ids32 != nullptr && i < npix)
+      if (len[k] != 0u)
       {
-        ids32[i] = id[k];
-      }
-      // one atomic per run of equal ids inside the 32-pixel group
-      const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, id[k], 1);
-      const bool head = (lane == 0) || (prev != id[k]);
-      const uint32_t headmask = __ballot_sync(0xFFFFFFFFu, head);
-      if (head && id[k] != INVALID_ID)
-      {
-        const uint32_t above = headmask & ~((2u << lane) - 1u);
-        const int next = above ? (__ffs(above) - 1) : 32;
         if (epoch != 0)
         {
           atomicMax(counts + id[k], tag);
         }
-        atomicAdd(counts + id[k], (uint32_t) (next - lane));
+        atomicAdd(counts + id[k], len[k]);
       }
     }
   }
@@ -238,6 +293,7 @@ struct ScatterArgs
   int stages;
   uint32_t count_mask;     // COUNT_MASK with a tagged epoch, 0xFFFFFFFF without
   uint32_t run_cap;        // power of two <= 32: runs of equal ids are cut every run_cap lanes
+  int mul_exact;           // mul: the reference's powf + logf sequence for every element (see neg_log_pow)
 
   float iew;
 };
@@ -442,10 +498,29 @@ __global__ void __launch_bounds__(288) scatter_kernel(ScatterArgs a)
 
     if constexpr (KIND == SMESH_KIND_SUMMAX)
     {
-      // one class per pixel (Fusion.cu:51-56): a single scalar reduction, no run merging needed
-      if (ok)
+      // one class per pixel (Fusion.cu:51-56): consecutive accepted pixels with the same face AND the same best class
+      // fold into one scalar reduction (segmented suffix sum over the run, log2(longest run) shuffle rounds)
+      const uint32_t key = ok ? id : INVALID_ID;
+      const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, key, 1);
+      const int prev_c = __shfl_up_sync(0xFFFFFFFFu, best_c, 1);
+      const bool head = ok && (lane == 0 || prev != key || prev_c != best_c);
+      const uint32_t headmask = __ballot_sync(0xFFFFFFFFu, head);
+      const uint32_t okmask = __ballot_sync(0xFFFFFFFFu, ok);
+      const uint32_t brk = (headmask | ~okmask) & ~((2u << lane) - 1u);
+      const int end = ok ? (brk ? (__ffs(brk) - 1) : 32) : lane + 1;
+      const int maxlen = (int) __reduce_max_sync(0xFFFFFFFFu, (unsigned) (head ? end - lane : 0));
+      float val = ok ? __fmul_rn(best, w) : 0.0f;
+      for (int d = 1; d < maxlen; d <<= 1)
       {
-        red_add_f32(a.acc + (size_t) id * Cpad + best_c, __fmul_rn(best, w));
+        const float t = __shfl_down_sync(0xFFFFFFFFu, val, d);
+        if (lane + d < end)
+        {
+          val = __fadd_rn(val, t);
+        }
+      }
+      if (head)
+      {
+        red_add_f32(a.acc + (size_t) id * Cpad + best_c, val);
       }
     }
     else
@@ -477,7 +552,7 @@ __global__ void __launch_bounds__(288) scatter_kernel(ScatterArgs a)
           }
           else
           {
-            v[k] = (k < nv && ok) ? neg_log_pow(v[k], w) : 0.0f;
+            v[k] = (k < nv && ok) ? neg_log_pow(v[k], w, a.mul_exact != 0) : 0.0f;
           }
         }
         // segmented suffix sum over the run (log2(longest run) shuffle rounds, warp-uniform)
@@ -698,8 +773,8 @@ __global__ void __launch_bounds__(LEAN ? 128 : 288, LEAN ? 8 : 0) scatter_pair_k
       }
       else
       {
-        A[k] = (k < C && okA) ? neg_log_pow(A[k], wA) : 0.0f;
-        B[k] = (k < C && okB) ? neg_log_pow(B[k], wB) : 0.0f;
+        A[k] = (k < C && okA) ? neg_log_pow(A[k], wA, a.mul_exact != 0) : 0.0f;
+        B[k] = (k < C && okB) ? neg_log_pow(B[k], wB, a.mul_exact != 0) : 0.0f;
       }
     }
 
@@ -1037,7 +1112,7 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(ScatterArgs a)
                 const int c = j + p * LG;
                 if (c < K)
                 {
-                  acc[p][k] = __fadd_rn(acc[p][k], neg_log_pow(v[u][p][k], wu[u]));
+                  acc[p][k] = __fadd_rn(acc[p][k], neg_log_pow(v[u][p][k], wu[u], a.mul_exact != 0));
                 }
               }
             }
@@ -1131,7 +1206,7 @@ __global__ void __launch_bounds__(256) scatter_direct_kernel(ScatterArgs a)
   }
   for (int c = 0; c < a.C; c++)
   {
-    red_add_f32(dst + c, KIND == SMESH_KIND_SUM ? __fmul_rn(row[c], w) : neg_log_pow(row[c], w));
+    red_add_f32(dst + c, KIND == SMESH_KIND_SUM ? __fmul_rn(row[c], w) : neg_log_pow(row[c], w, a.mul_exact != 0));
   }
 }
 
@@ -1139,17 +1214,11 @@ __global__ void __launch_bounds__(256) scatter_direct_kernel(ScatterArgs a)
 // get(): per-face class distribution
 // ---------------------------------------------------------------------------------------------------------------------
 
+// One accumulator row -> its distribution, in place (row[0 .. C) with element stride 1): mul: exp(-(l - min l)), then the
+// reference's sequential L1 norm, v * (1 / norm), NaN/Inf -> 0 (Fusion.cu:66-92, Fusion.h:79-104).
 template <int KIND>
-__global__ void __launch_bounds__(256) get_kernel(const float* __restrict__ acc, int64_t P, int C, int Cpad,
-                                                  float* __restrict__ out)
+__device__ __forceinline__ void get_row(float* row, int C)
 {
-  const int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= P)
-  {
-    return;
-  }
-  const float* row = acc + (size_t) r * Cpad;
-  float* o = out + (size_t) r * C;
   float best = CUDART_INF_F;
   bool have = false;
   if (KIND == SMESH_KIND_MUL)
@@ -1173,17 +1242,133 @@ __global__ void __launch_bounds__(256) get_kernel(const float* __restrict__ acc,
     if (KIND == SMESH_KIND_MUL)
     {
       v = (!have || isinf(v)) ? 0.0f : expf(-__fsub_rn(v, best));
-      o[c] = v; // parked, rescaled below
+      row[c] = v;
     }
     norm = __fadd_rn(norm, fabsf(v));
   }
   const float inv = __fdiv_rn(1.0f, norm);
   for (int c = 0; c < C; c++)
   {
-    const float v = (KIND == SMESH_KIND_MUL) ? o[c] : row[c];
-    const float x = __fmul_rn(v, inv);
-    o[c] = (isnan(x) || isinf(x)) ? 0.0f : x; // Fusion.h:79-95
+    const float x = __fmul_rn(row[c], inv);
+    row[c] = (isnan(x) || isinf(x)) ? 0.0f : x; // Fusion.h:79-95
   }
+}
+
+// get(): HBM-bound (read P x Cpad, write P x C floats). A CTA stages `rows` accumulator rows in shared memory with
+// 128-bit coalesced loads (row stride Cpad + 1 words: a thread per row then walks its row without bank conflicts), one
+// thread per row turns it into the distribution in place in the reference's sequential order, and the block of rows
+// leaves as one contiguous run of rows * C floats with 128-bit coalesced stores.
+template <int KIND>
+__global__ void __launch_bounds__(256) get_kernel(const float* __restrict__ acc, int64_t P, int C, int Cpad, int rows,
+                                                  float* __restrict__ out)
+{
+  extern __shared__ __align__(16) float get_smem[];
+  const int stride = Cpad + 1;
+  const int64_t nblocks = (P + rows - 1) / rows;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x)
+  {
+    const int64_t r0 = blk * rows;
+    const int n = (int) min((int64_t) rows, P - r0);
+    const int chunks = Cpad >> 2;                       // float4 per row
+    const float4* src = reinterpret_cast<const float4*>(acc + (size_t) r0 * Cpad);
+    for (int i = threadIdx.x; i < n * chunks; i += blockDim.x)
+    {
+      const float4 v = __ldcs(src + i);
+      const int r = i / chunks, j = i - r * chunks;
+      float* d = get_smem + r * stride + 4 * j;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < n; r += blockDim.x)
+    {
+      get_row<KIND>(get_smem + r * stride, C);
+    }
+    __syncthreads();
+    float* dst = out + (size_t) r0 * C;
+    const int total = n * C;
+    if (((reinterpret_cast<uintptr_t>(dst) & 15) == 0))
+    {
+      const int total4 = total >> 2;
+      for (int i = threadIdx.x; i < total4; i += blockDim.x)
+      {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+          const int e = 4 * i + k;
+          const int r = e / C;
+          v[k] = get_smem[r * stride + (e - r * C)];
+        }
+        __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(v[0], v[1], v[2], v[3]));
+      }
+      for (int e = (total4 << 2) + threadIdx.x; e < total; e += blockDim.x)
+      {
+        const int r = e / C;
+        dst[e] = get_smem[r * stride + (e - r * C)];
+      }
+    }
+    else
+    {
+      for (int e = threadIdx.x; e < total; e += blockDim.x)
+      {
+        const int r = e / C;
+        dst[e] = get_smem[r * stride + (e - r * C)];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// class vectors too wide for the staged kernel: one thread per row straight from global memory
+template <int KIND>
+__global__ void __launch_bounds__(256) get_direct_kernel(const float* __restrict__ acc, int64_t P, int C, int Cpad,
+                                                         float* __restrict__ out)
+{
+  const int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P)
+  {
+    return;
+  }
+  const float* row = acc + (size_t) r * Cpad;
+  float* o = out + (size_t) r * C;
+  for (int c = 0; c < C; c++)
+  {
+    o[c] = row[c];
+  }
+  get_row<KIND>(o, C);
+}
+
+template <int KIND>
+static int launch_get(const float* acc, int64_t P, int C, float* out, cudaStream_t stream)
+{
+  const int Cpad = smesh_fuse_padded_classes(C);
+  // rows per CTA: 256 if they fit in ~96 KB (two CTAs per SM), else whatever fits in 200 KB, in whole warps
+  const size_t row_bytes = (size_t) (Cpad + 1) * 4;
+  int rows = 256;
+  if (rows * row_bytes > 96 * 1024)
+  {
+    rows = (int) ((200 * 1024) / row_bytes) / 32 * 32;
+  }
+  if (rows < 32)
+  {
+    get_direct_kernel<KIND><<<(unsigned) ((P + 255) / 256), 256, 0, stream>>>(acc, P, C, Cpad, out);
+    SMESH_LAUNCH_CHECK("get_direct_kernel");
+    return SMESH_OK;
+  }
+  const size_t smem = (size_t) rows * row_bytes;
+  auto kernel = get_kernel<KIND>;
+  int blocks_per_sm = 0;
+  const int rc = kernel_blocks_per_sm(reinterpret_cast<const void*>(kernel), 256, smem, &blocks_per_sm);
+  if (rc != SMESH_OK)
+  {
+    return rc;
+  }
+  int64_t blocks = (P + rows - 1) / rows;
+  const int64_t cap = (int64_t) num_sms() * (blocks_per_sm > 0 ? blocks_per_sm : 1);
+  if (blocks > cap) blocks = cap;
+  kernel<<<(unsigned) blocks, 256, smem, stream>>>(acc, P, C, Cpad, rows, out);
+  SMESH_LAUNCH_CHECK("get_kernel");
+  return SMESH_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1232,25 +1417,17 @@ static int launch_scatter_ring(const ScatterArgs& args_in, const RingConfig& cfg
   ScatterArgs args = args_in;
   const size_t smem = ring_smem_bytes(args.C, cfg);
   auto kernel = scatter_kernel<KIND, CT>;
-  static thread_local size_t configured_smem = 0;
-  static thread_local int blocks_per_sm = 0;
-  static thread_local int configured_threads = 0;
-  static thread_local int configured_device = -1;
   const int threads = (cfg.consumer_warps + 1) * 32;
-  int device = 0;
-  SMESH_CUDA_CHECK(cudaGetDevice(&device));
-  if (configured_smem != smem || configured_threads != threads || configured_device != device)
+  int blocks_per_sm = 0;
+  const int cfg_rc = kernel_blocks_per_sm(reinterpret_cast<const void*>(kernel), threads, smem, &blocks_per_sm);
+  if (cfg_rc != SMESH_OK)
   {
-    SMESH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    SMESH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, threads, smem));
-    if (blocks_per_sm < 1)
-    {
-      set_error("scatter_kernel does not fit on an SM (C=%d, %zu bytes of shared memory)", args.C, smem);
-      return SMESH_ERR_UNSUPPORTED;
-    }
-    configured_smem = smem;
-    configured_threads = threads;
-    configured_device = device;
+    return cfg_rc;
+  }
+  if (blocks_per_sm < 1)
+  {
+    set_error("scatter_kernel does not fit on an SM (C=%d, %zu bytes of shared memory)", args.C, smem);
+    return SMESH_ERR_UNSUPPORTED;
   }
   const int tile_px = cfg.consumer_warps * 32;
   args.ntiles = (args.npix + tile_px - 1) / tile_px;
@@ -1300,25 +1477,17 @@ static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
   const size_t smem = (size_t) cfg.stages * cfg.consumer_warps * 64 * CT * 4 + (size_t) cfg.stages * 16 +
                       (size_t) cfg.consumer_warps * (64 * ((CT + 3) & ~3) + 64) * 4; // flush rows + their face ids
   auto kernel = scatter_pair_kernel<KIND, CT, LEAN>;
-  static thread_local size_t configured_smem = 0;
-  static thread_local int blocks_per_sm = 0;
-  static thread_local int configured_threads = 0;
-  static thread_local int configured_device = -1;
   const int threads = (cfg.consumer_warps + 1) * 32;
-  int device = 0;
-  SMESH_CUDA_CHECK(cudaGetDevice(&device));
-  if (configured_smem != smem || configured_threads != threads || configured_device != device)
+  int blocks_per_sm = 0;
+  const int cfg_rc = kernel_blocks_per_sm(reinterpret_cast<const void*>(kernel), threads, smem, &blocks_per_sm);
+  if (cfg_rc != SMESH_OK)
   {
-    SMESH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    SMESH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, threads, smem));
-    if (blocks_per_sm < 1)
-    {
-      set_error("scatter_pair_kernel does not fit on an SM (%zu bytes of shared memory)", smem);
-      return SMESH_ERR_UNSUPPORTED;
-    }
-    configured_smem = smem;
-    configured_threads = threads;
-    configured_device = device;
+    return cfg_rc;
+  }
+  if (blocks_per_sm < 1)
+  {
+    set_error("scatter_pair_kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+    return SMESH_ERR_UNSUPPORTED;
   }
   const int tile_px = cfg.consumer_warps * 64;
   args.ntiles = (args.npix + tile_px - 1) / tile_px;
@@ -1382,29 +1551,28 @@ static int launch_scatter(const ScatterArgs& args, cudaStream_t stream)
 }
 
 template <typename IdT>
-static int launch_count(const void* ids, int64_t so, int64_t si, int64_t n_inner, int64_t npix, int64_t P, uint32_t* counts,
-                        uint32_t* ids32, bool flat, uint32_t epoch, cudaStream_t stream)
+static int launch_count(const void* ids, int64_t so, int64_t si, int64_t n_outer, int64_t n_inner, int64_t P, uint32_t* counts,
+                        uint32_t* ids32, uint32_t epoch, cudaStream_t stream)
 {
-  const int64_t per_block = (256 / 32) * 32 * COUNT_UNROLL;
-  int64_t blocks = (npix + per_block - 1) / per_block;
+  const int64_t items = ((n_inner + 31) / 32) * ((n_outer + COUNT_COLS - 1) / COUNT_COLS); // one warp each
+  int64_t blocks = (items + 7) / 8;
   const int64_t cap = (int64_t) num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  count_kernel<IdT><<<(unsigned) blocks, 256, 0, stream>>>(static_cast<const IdT*>(ids), so, si, n_inner, npix, P, counts,
-                                                           ids32, flat ? 1 : 0, epoch);
+  count_kernel<IdT><<<(unsigned) blocks, 256, 0, stream>>>(static_cast<const IdT*>(ids), so, si, n_outer, n_inner, P, counts,
+                                                           ids32, epoch);
   SMESH_LAUNCH_CHECK("count_kernel");
   return SMESH_OK;
 }
 
-static int launch_count_any(const char* fn, int id_dtype, const void* ids, int64_t so, int64_t si, int64_t n_inner,
-                            int64_t npix, int64_t P, uint32_t* counts, uint32_t* ids32, bool flat, uint32_t epoch,
-                            cudaStream_t stream)
+static int launch_count_any(const char* fn, int id_dtype, const void* ids, int64_t so, int64_t si, int64_t n_outer,
+                            int64_t n_inner, int64_t P, uint32_t* counts, uint32_t* ids32, uint32_t epoch, cudaStream_t stream)
 {
   switch (id_dtype)
   {
-    case SMESH_ID_U32: return launch_count<uint32_t>(ids, so, si, n_inner, npix, P, counts, ids32, flat, epoch, stream);
-    case SMESH_ID_I32: return launch_count<int32_t>(ids, so, si, n_inner, npix, P, counts, ids32, flat, epoch, stream);
-    case SMESH_ID_U64: return launch_count<uint64_t>(ids, so, si, n_inner, npix, P, counts, ids32, flat, epoch, stream);
-    case SMESH_ID_I64: return launch_count<int64_t>(ids, so, si, n_inner, npix, P, counts, ids32, flat, epoch, stream);
+    case SMESH_ID_U32: return launch_count<uint32_t>(ids, so, si, n_outer, n_inner, P, counts, ids32, epoch, stream);
+    case SMESH_ID_I32: return launch_count<int32_t>(ids, so, si, n_outer, n_inner, P, counts, ids32, epoch, stream);
+    case SMESH_ID_U64: return launch_count<uint64_t>(ids, so, si, n_outer, n_inner, P, counts, ids32, epoch, stream);
+    case SMESH_ID_I64: return launch_count<int64_t>(ids, so, si, n_outer, n_inner, P, counts, ids32, epoch, stream);
     default: set_error("%s: unknown id dtype %d", fn, id_dtype); return SMESH_ERR_INVALID_ARGUMENT;
   }
 }
@@ -1441,6 +1609,8 @@ static ScatterArgs make_scatter_args(const uint32_t* ids32, const float* probs, 
   args.stages = 0;
   args.count_mask = epoch != 0 ? COUNT_MASK : 0xFFFFFFFFu;
   args.run_cap = scatter_run_cap();
+  const char* mul_exact_env = getenv("SMESH_MUL_EXACT"); // read per call: tests switch it
+  args.mul_exact = (mul_exact_env != nullptr && atoi(mul_exact_env) != 0) ? 1 : 0;
   args.iew = iew;
   return args;
 }
@@ -1456,16 +1626,51 @@ static int launch_scatter_kind(int kind, const ScatterArgs& args, cudaStream_t s
   }
 }
 
-static int add_view(int kind, const void* ids, int id_dtype, int64_t ids_so, int64_t ids_si, const float* probs,
-                    const float* weights, int64_t w_so, int64_t w_si, int64_t n_outer, int64_t n_inner, int C, int64_t P,
-                    float iew, uint32_t* counts, uint32_t* ids32, float* acc, uint32_t epoch, cudaStream_t stream)
+// One view = two stages on possibly different streams: the per-face pixel count (Mesh.h:90-93) and the gated, weighted
+// scatter (Mesh.h:94-106).
+struct ViewStages
 {
-  const int64_t npix = n_outer * n_inner;
-  if (npix == 0 || P == 0)
+  int kind, id_dtype, C;
+  const void* ids;
+  int64_t ids_so, ids_si, n_outer, n_inner, P;
+  const float* probs;
+  const float* weights;
+  float iew;
+  uint32_t* ids32;
+  float* acc;
+  bool zero_copy; // 32-bit ids already in flat order are consumed in place
+
+  int64_t npix() const { return n_outer * n_inner; }
+  const uint32_t* flat_ids() const { return zero_copy ? static_cast<const uint32_t*>(ids) : ids32; }
+
+  int count(uint32_t* counts, uint32_t epoch, cudaStream_t stream) const
   {
+    return launch_count_any("smesh_fuse_add", id_dtype, ids, ids_so, ids_si, n_outer, n_inner, P, counts,
+                            zero_copy ? nullptr : ids32, epoch, stream);
+  }
+
+  int scatter(uint32_t* counts, uint32_t epoch, cudaStream_t stream) const
+  {
+    const int rc = launch_scatter_kind(kind, make_scatter_args(flat_ids(), probs, weights, counts, acc, npix(), C, P, iew, epoch),
+                                       stream);
+    if (rc != SMESH_OK)
+    {
+      return rc;
+    }
+    if (epoch == 0)
+    {
+      clear_kernel<<<(unsigned) ((npix() + 255) / 256), 256, 0, stream>>>(flat_ids(), npix(), P, counts);
+      SMESH_LAUNCH_CHECK("clear_kernel");
+    }
     return SMESH_OK;
   }
-  int rc = check_epoch("smesh_fuse_add", epoch, npix);
+};
+
+static int make_view(const char* fn, ViewStages& v, int kind, const void* ids, int id_dtype, int64_t ids_so, int64_t ids_si,
+                     const float* probs, const float* weights, int64_t w_so, int64_t w_si, int64_t n_outer, int64_t n_inner,
+                     int C, int64_t P, float iew, uint32_t* ids32, float* acc, uint32_t epoch)
+{
+  const int rc = check_epoch(fn, epoch, n_outer * n_inner);
   if (rc != SMESH_OK)
   {
     return rc;
@@ -1475,30 +1680,72 @@ static int add_view(int kind, const void* ids, int id_dtype, int64_t ids_so, int
     const bool w_flat = (w_si == 1 || n_inner == 1) && (w_so == n_inner || n_outer == 1);
     if (!w_flat)
     {
-      set_error("smesh_fuse_add: the weights image must be contiguous in the same pixel order as the probability image");
+      set_error("%s: the weights image must be contiguous in the same pixel order as the probability image", fn);
       return SMESH_ERR_UNSUPPORTED;
     }
   }
   const bool ids_flat = (ids_si == 1 || n_inner == 1) && (ids_so == n_inner || n_outer == 1);
-  // 32-bit ids already in flat order are consumed in place (int32: negative values read as >= 2^31 and fail `id < P`)
-  const bool zero_copy = ids_flat && (id_dtype == SMESH_ID_U32 || (id_dtype == SMESH_ID_I32 && P <= 0x7FFFFFFFll));
-  rc = launch_count_any("smesh_fuse_add", id_dtype, ids, ids_so, ids_si, n_inner, npix, P, counts, zero_copy ? nullptr : ids32,
-                        ids_flat, epoch, stream);
+  v.kind = kind; v.id_dtype = id_dtype; v.C = C;
+  v.ids = ids; v.ids_so = ids_so; v.ids_si = ids_si; v.n_outer = n_outer; v.n_inner = n_inner; v.P = P;
+  v.probs = probs; v.weights = weights; v.iew = iew; v.ids32 = ids32; v.acc = acc;
+  // (int32: negative values read as >= 2^31 and fail `id < P`)
+  v.zero_copy = ids_flat && (id_dtype == SMESH_ID_U32 || (id_dtype == SMESH_ID_I32 && P <= 0x7FFFFFFFll));
+  return SMESH_OK;
+}
+
+static int add_view(int kind, const void* ids, int id_dtype, int64_t ids_so, int64_t ids_si, const float* probs,
+                    const float* weights, int64_t w_so, int64_t w_si, int64_t n_outer, int64_t n_inner, int C, int64_t P,
+                    float iew, uint32_t* counts, uint32_t* ids32, float* acc, uint32_t epoch, cudaStream_t stream)
+{
+  if (n_outer * n_inner == 0 || P == 0)
+  {
+    return SMESH_OK;
+  }
+  ViewStages v;
+  int rc = make_view("smesh_fuse_add", v, kind, ids, id_dtype, ids_so, ids_si, probs, weights, w_so, w_si, n_outer, n_inner, C, P,
+                     iew, ids32, acc, epoch);
   if (rc != SMESH_OK)
   {
     return rc;
   }
-  const uint32_t* ids_flat_ptr = zero_copy ? static_cast<const uint32_t*>(ids) : ids32;
-  rc = launch_scatter_kind(kind, make_scatter_args(ids_flat_ptr, probs, weights, counts, acc, npix, C, P, iew, epoch), stream);
-  if (rc != SMESH_OK)
+  rc = v.count(counts, epoch, stream);
+  return rc != SMESH_OK ? rc : v.scatter(counts, epoch, stream);
+}
+
+// Side stream of smesh_fuse_add_batch (one per host thread and device, created on first use and kept): the count stage
+// of view b+1 runs on it while the scatter stage of view b runs on the caller's stream. Fork and join are event waits,
+// so the pattern is also legal inside a stream capture (the side stream joins the capture and leaves it again).
+struct SideStream
+{
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr;
+  cudaEvent_t counted[2] = {nullptr, nullptr};
+  cudaEvent_t scattered[2] = {nullptr, nullptr};
+};
+
+static int side_stream(SideStream** out)
+{
+  constexpr int MAX_DEVICES = 64;
+  static thread_local SideStream table[MAX_DEVICES];
+  int device = 0;
+  SMESH_CUDA_CHECK(cudaGetDevice(&device));
+  if (device < 0 || device >= MAX_DEVICES)
   {
-    return rc;
+    *out = nullptr;
+    return SMESH_OK;
   }
-  if (epoch == 0)
+  SideStream& s = table[device];
+  if (s.stream == nullptr)
   {
-    clear_kernel<<<(unsigned) ((npix + 255) / 256), 256, 0, stream>>>(ids_flat_ptr, npix, P, counts);
-    SMESH_LAUNCH_CHECK("clear_kernel");
+    SMESH_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    SMESH_CUDA_CHECK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++)
+    {
+      SMESH_CUDA_CHECK(cudaEventCreateWithFlags(&s.counted[i], cudaEventDisableTiming));
+      SMESH_CUDA_CHECK(cudaEventCreateWithFlags(&s.scattered[i], cudaEventDisableTiming));
+    }
   }
+  *out = &s;
   return SMESH_OK;
 }
 
@@ -1568,9 +1815,8 @@ extern "C" int smesh_fuse_count(const void* ids, int id_dtype, int64_t ids_strid
   {
     return rc;
   }
-  const bool flat = (ids_stride_inner == 1 || n_inner == 1) && (ids_stride_outer == n_inner || n_outer == 1);
-  return launch_count_any("smesh_fuse_count", id_dtype, ids, ids_stride_outer, ids_stride_inner, n_inner, npix, P, counts,
-                          ids32_out, flat, count_epoch, static_cast<cudaStream_t>(stream_v));
+  return launch_count_any("smesh_fuse_count", id_dtype, ids, ids_stride_outer, ids_stride_inner, n_outer, n_inner, P, counts,
+                          ids32_out, count_epoch, static_cast<cudaStream_t>(stream_v));
 }
 
 extern "C" int smesh_fuse_scatter(int kind, const uint32_t* ids32, const float* probs, const float* weights, int64_t n_pix,
@@ -1620,10 +1866,10 @@ extern "C" int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id
                                     int64_t ids_stride_outer, int64_t ids_stride_inner, const float* probs,
                                     int64_t probs_stride_view, const float* weights, int64_t w_stride_view,
                                     int64_t w_stride_outer, int64_t w_stride_inner, int64_t n_outer, int64_t n_inner, int C,
-                                    int64_t P, float iew, uint32_t* counts, uint32_t count_epoch0, uint32_t* ids32, float* acc,
-                                    void* stream)
+                                    int64_t P, float iew, uint32_t* counts2, uint32_t count_epoch0, uint32_t* ids32, float* acc,
+                                    void* stream_v)
 {
-  int rc = check_add_args("smesh_fuse_add_batch", kind, ids, probs, n_outer, n_inner, C, P, counts, ids32, acc);
+  int rc = check_add_args("smesh_fuse_add_batch", kind, ids, probs, n_outer, n_inner, C, P, counts2, ids32, acc);
   if (rc != SMESH_OK)
   {
     return rc;
@@ -1634,18 +1880,103 @@ extern "C" int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id
               count_epoch0);
     return SMESH_ERR_INVALID_ARGUMENT;
   }
-  const size_t id_size = (id_dtype == SMESH_ID_U64 || id_dtype == SMESH_ID_I64) ? 8 : 4;
-  for (int64_t b = 0; b < B; b++)
+  if (B == 0 || n_outer * n_inner == 0 || P == 0)
   {
+    return SMESH_OK;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const size_t id_size = (id_dtype == SMESH_ID_U64 || id_dtype == SMESH_ID_I64) ? 8 : 4;
+  auto view = [&](int64_t b, ViewStages& v) -> int {
     const void* ids_b = static_cast<const char*>(ids) + (size_t) b * ids_stride_view * id_size;
     const float* probs_b = probs + (size_t) b * probs_stride_view;
     const float* weights_b = weights ? weights + (size_t) b * w_stride_view : nullptr;
-    rc = add_view(kind, ids_b, id_dtype, ids_stride_outer, ids_stride_inner, probs_b, weights_b, w_stride_outer,
-                  w_stride_inner, n_outer, n_inner, C, P, iew, counts, ids32, acc,
-                  count_epoch0 != 0 ? count_epoch0 + (uint32_t) b : 0u, static_cast<cudaStream_t>(stream));
+    return make_view("smesh_fuse_add_batch", v, kind, ids_b, id_dtype, ids_stride_outer, ids_stride_inner, probs_b, weights_b,
+                     w_stride_outer, w_stride_inner, n_outer, n_inner, C, P, iew, ids32, acc, count_epoch0);
+  };
+  // tagged mode: view b counts into array (epoch & 1); untagged mode: array 0 only (it is clean again after every view)
+  auto epoch_of = [&](int64_t b) -> uint32_t { return count_epoch0 != 0 ? count_epoch0 + (uint32_t) b : 0u; };
+  auto counts_of = [&](int64_t b) -> uint32_t* { return counts2 + (size_t) (epoch_of(b) & 1u) * (size_t) P; };
+
+  ViewStages v0;
+  rc = view(0, v0);
+  if (rc != SMESH_OK)
+  {
+    return rc;
+  }
+  static const bool no_overlap = getenv("SMESH_NO_BATCH_OVERLAP") != nullptr; // profiling only
+  SideStream* side = nullptr;
+  // overlap needs tagged counters (two arrays in flight) and ids that are consumed in place (one ids32 scratch)
+  if (B >= 2 && count_epoch0 != 0 && v0.zero_copy && !no_overlap)
+  {
+    rc = side_stream(&side);
     if (rc != SMESH_OK)
     {
       return rc;
+    }
+  }
+  if (side == nullptr)
+  {
+    for (int64_t b = 0; b < B; b++)
+    {
+      ViewStages v;
+      rc = view(b, v);
+      if (rc == SMESH_OK) rc = v.count(counts_of(b), epoch_of(b), stream);
+      if (rc == SMESH_OK) rc = v.scatter(counts_of(b), epoch_of(b), stream);
+      if (rc != SMESH_OK)
+      {
+        return rc;
+      }
+    }
+    return SMESH_OK;
+  }
+  // count(b + 1) on the side stream under scatter(b) on the caller's stream. count(b + 1) writes the array scatter(b - 1)
+  // read, so it waits for that scatter; scatter(b + 1) waits for count(b + 1). The last event the caller's stream waits
+  // for is the side stream's last operation: the side stream has joined when the call returns.
+  SMESH_CUDA_CHECK(cudaEventRecord(side->fork, stream));
+  SMESH_CUDA_CHECK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  rc = v0.count(counts_of(0), epoch_of(0), stream);
+  if (rc != SMESH_OK)
+  {
+    return rc;
+  }
+  for (int64_t b = 0; b < B; b++)
+  {
+    ViewStages v, vn;
+    rc = view(b, v);
+    if (rc != SMESH_OK)
+    {
+      return rc;
+    }
+    if (b + 1 < B)
+    {
+      rc = view(b + 1, vn);
+      if (rc != SMESH_OK)
+      {
+        return rc;
+      }
+      if (b >= 1)
+      {
+        SMESH_CUDA_CHECK(cudaStreamWaitEvent(side->stream, side->scattered[(b - 1) & 1], 0));
+      }
+      rc = vn.count(counts_of(b + 1), epoch_of(b + 1), side->stream);
+      if (rc != SMESH_OK)
+      {
+        return rc;
+      }
+      SMESH_CUDA_CHECK(cudaEventRecord(side->counted[(b + 1) & 1], side->stream));
+    }
+    if (b >= 1)
+    {
+      SMESH_CUDA_CHECK(cudaStreamWaitEvent(stream, side->counted[b & 1], 0));
+    }
+    rc = v.scatter(counts_of(b), epoch_of(b), stream);
+    if (rc != SMESH_OK)
+    {
+      return rc;
+    }
+    if (b + 2 < B)
+    {
+      SMESH_CUDA_CHECK(cudaEventRecord(side->scattered[b & 1], stream));
     }
   }
   return SMESH_OK;
@@ -1663,16 +1994,12 @@ extern "C" int smesh_fuse_get(int kind, const float* acc, int64_t P, int C, floa
     return SMESH_OK;
   }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  const int Cpad = smesh_fuse_padded_classes(C);
-  const unsigned blocks = (unsigned) ((P + 255) / 256);
   switch (kind)
   {
-    case SMESH_KIND_SUM: get_kernel<SMESH_KIND_SUM><<<blocks, 256, 0, stream>>>(acc, P, C, Cpad, out); break;
-    case SMESH_KIND_SUMMAX: get_kernel<SMESH_KIND_SUMMAX><<<blocks, 256, 0, stream>>>(acc, P, C, Cpad, out); break;
-    default: get_kernel<SMESH_KIND_MUL><<<blocks, 256, 0, stream>>>(acc, P, C, Cpad, out); break;
+    case SMESH_KIND_SUM: return launch_get<SMESH_KIND_SUM>(acc, P, C, out, stream);
+    case SMESH_KIND_SUMMAX: return launch_get<SMESH_KIND_SUMMAX>(acc, P, C, out, stream);
+    default: return launch_get<SMESH_KIND_MUL>(acc, P, C, out, stream);
   }
-  SMESH_LAUNCH_CHECK("get_kernel");
-  return SMESH_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

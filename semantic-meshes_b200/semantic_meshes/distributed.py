@@ -22,3 +22,34 @@ def allreduce_accumulator(acc, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
     return acc
+
+
+def row_slices(n_rows, world_size):
+    """Equal row blocks (the last ones padded): rank r owns rows [r * per, min((r + 1) * per, n_rows))."""
+    per = (n_rows + world_size - 1) // world_size
+    return per, [(min(r * per, n_rows), min((r + 1) * per, n_rows)) for r in range(world_size)]
+
+
+def reduce_scatter_rows(acc, group=None):
+    """Sum the (P, Cpad) accumulators of all ranks and leave every rank with the rows of its own slice only: one
+    reduce-scatter, (N-1)/N x P x Cpad floats on the wire per rank instead of the all-reduce's 2 (N-1)/N.
+    -> ((first, last), tensor of those summed rows). Without a process group: the whole accumulator."""
+    import torch
+    import torch.distributed as dist
+    P = acc.shape[0]
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return (0, P), acc
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    per, slices = row_slices(P, world)
+    src = acc
+    if per * world != P:  # pad to equal blocks
+        src = torch.zeros((per * world,) + tuple(acc.shape[1:]), dtype=acc.dtype, device=acc.device)
+        src[:P] = acc
+    first, last = slices[rank]
+    if not acc.is_cuda:  # gloo (the CPU tests) has no reduce-scatter: all-reduce a copy and cut the slice out
+        total = src.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        return (first, last), total[first:last]
+    out = torch.empty((per,) + tuple(acc.shape[1:]), dtype=acc.dtype, device=acc.device)
+    dist.reduce_scatter_tensor(out, src.contiguous(), op=dist.ReduceOp.SUM, group=group)
+    return (first, last), out[:last - first]

@@ -5,7 +5,8 @@
     annotations = aggregator.get()                          # (P, C) float32 numpy
 
 Semantics of include/semantic_meshes/fusion/Mesh.h:57-133 with the aggregator chains of Fusion.cu:46-92 ("sum",
-"summax", "mul"). The accumulator lives on the GPU as a torch tensor; `add` is asynchronous on the current CUDA stream.
+"summax", "mul"). The accumulator lives on the GPU as a torch tensor; `add` is asynchronous on the current CUDA stream
+(host inputs have been read when it returns, like the reference's synchronous add; see `async_host_inputs`).
 Views may be sharded over several processes / GPUs: every rank adds its views, then `allreduce()` sums the
 accumulators (one NCCL all-reduce) before `get()`.
 """
@@ -56,6 +57,15 @@ class MeshAggregator:
         self._ids32 = torch.empty((0,), dtype=torch.int32, device=self.device)
         self._epoch = 0      # last count epoch handed out (see include/smesh.h: tagged per-view pixel counters)
         self._epoch_gen = 0  # bumped whenever the counters are zeroed: tokens of earlier counted renders become void
+        self._array_epoch = [0, 0]  # epoch last counted into each of the two arrays (a token is valid only while its
+        #                             array still holds its view)
+        # streams that have touched the counters since they were last zeroed, and the event of that zeroing: a reset on
+        # one stream is ordered against the users on the others (render(count_into=...) runs on a render stream)
+        self._users, self._reset_event, self._reset_stream, self._reset_captured = set(), None, None, False
+        # False (default): a pinned host tensor passed to add() has been copied when add() returns, like the reference's
+        # synchronous add - the caller may refill it right away. True: the copy is left in flight (tensor.to(device,
+        # non_blocking=True) semantics), the caller must not touch the buffer before the stream has caught up.
+        self.async_host_inputs = False
         # upload path of host predictions (see _upload_probs)
         self._copy_stream, self._stage_bufs, self._stage_done, self._stage_next, self._stage_last = None, [None, None], [None, None], 0, None
 
@@ -102,6 +112,8 @@ class MeshAggregator:
                 up.record(cs)
             main.wait_event(up)
             self._stage_last = k
+            if host.is_pinned() and not self.async_host_inputs:
+                up.synchronize()  # pageable memory is staged by the driver before copy_ returns; pinned memory is not
         return buf
 
     def _release_stage(self):
@@ -172,10 +184,44 @@ class MeshAggregator:
     def restart_epochs(self):
         """Zero the per-view pixel counters and start the count epochs over. Called automatically when the 8-bit epoch
         wraps; call it yourself at the start of any region you capture into a CUDA graph, so every replay sees the same
-        epochs on clean counters."""
+        epochs on clean counters. The zero-fill runs on the current stream after everything the other streams have
+        enqueued on the counters so far (counted renders run on a render stream), and later users on other streams wait
+        for it."""
+        torch = self._torch
+        cur = torch.cuda.current_stream(self.device)
+        capturing = torch.cuda.is_current_stream_capturing()
+        others = [s for s in self._users if s != cur and self._may_wait_for(s, capturing)]
+        for s in others:
+            cur.wait_stream(s)
         self._counts2.zero_()
+        self._reset_event = None
+        if others:
+            self._reset_event = torch.cuda.Event()
+            self._reset_event.record(cur)
+        self._reset_stream, self._reset_captured = cur, capturing
+        self._users = {cur}
         self._epoch = 0
         self._epoch_gen += 1
+        self._array_epoch = [0, 0]
+
+    def _may_wait_for(self, stream, capturing):
+        """While the current stream is being captured into a CUDA graph only streams of the same capture may be waited
+        for (a dependency on work outside the capture cannot be expressed; whoever captures starts from a quiet device)."""
+        if not capturing:
+            return True
+        with self._torch.cuda.stream(stream):
+            return self._torch.cuda.is_current_stream_capturing()
+
+    def _enter(self):
+        """Before anything that reads or writes the counters is enqueued on the current stream."""
+        torch = self._torch
+        cur = torch.cuda.current_stream(self.device)
+        if cur not in self._users:
+            ev = self._reset_event
+            # (an event recorded inside a capture means something only to streams of that capture)
+            if ev is not None and cur != self._reset_stream and self._reset_captured == torch.cuda.is_current_stream_capturing():
+                cur.wait_event(ev)
+            self._users.add(cur)
 
     def _counts_for(self, epoch):
         return self._counts2[epoch & 1]
@@ -191,11 +237,15 @@ class MeshAggregator:
         if npix >= (1 << 24):
             if self._epoch != 0:
                 self.restart_epochs()
+            self._enter()
             return 0
         if self._epoch + n > 255:
             self.restart_epochs()
+        self._enter()
         first = self._epoch + 1
         self._epoch += n
+        for e in range(max(first, self._epoch - 1), self._epoch + 1):
+            self._array_epoch[e & 1] = e
         return first
 
     def _scratch(self, npix):
@@ -209,9 +259,9 @@ class MeshAggregator:
         `renderer.render(camera, count_into=self)` the per-face pixel counts are already in place and only the scatter
         stage runs.
 
-        The call is asynchronous on the current CUDA stream (the reference's is synchronous). Inputs in pageable host memory
-        (numpy arrays) have been read when it returns; a PINNED host tensor is read by an asynchronous copy, like
-        `tensor.to(device, non_blocking=True)`: do not overwrite it before the stream has caught up."""
+        The kernels are asynchronous on the current CUDA stream (the reference's add is synchronous); host inputs have
+        been read when the call returns, so the caller may reuse its buffers like with the reference (set
+        `async_host_inputs = True` to leave the copy of a PINNED host tensor in flight instead)."""
         torch = self._torch
         ids, id_dtype, pr, wt = self._stage(primitive_indices, probs, weights)
         lay = self._layout(ids, pr, wt)
@@ -221,8 +271,10 @@ class MeshAggregator:
         stream = torch.cuda.current_stream().cuda_stream
         token = getattr(primitive_indices, "_smesh_counted", None)
         if (token is not None and token[0] == id(self) and token[1] == self._epoch_gen and ids.dtype == torch.int32
+                and self._array_epoch[token[2] & 1] == token[2]  # no later view has counted into that array since
                 and (ids_si == 1 or n_inner == 1) and (ids_so == n_inner or n_outer == 1)):
             epoch = token[2]
+            self._enter()
             with torch.cuda.device(self.device):
                 rc = _lib.lib.smesh_fuse_scatter(self._kind, ids.data_ptr(), pr.data_ptr(),
                                                  wt.data_ptr() if wt is not None else None, n_outer * n_inner, self.classes,
@@ -243,7 +295,8 @@ class MeshAggregator:
 
     def add_batch(self, primitive_indices, probs, weights=None):
         """Extension: fuse B views held in batched device tensors (B,W,H) / (B,W,H,C) / (B,W,H) with one call; the same
-        result as B `add` calls in order, without B trips through Python."""
+        result as B `add` calls in order, without B trips through Python - and with the count stage of view b+1 running
+        on a side stream under the scatter stage of view b (smesh_fuse_add_batch)."""
         torch = self._torch
         ids = self._as_tensor(primitive_indices, "primitive_indices")
         pr = self._as_tensor(probs, "probs")
@@ -260,8 +313,13 @@ class MeshAggregator:
         pr0c, wt0c, n_outer, n_inner, ids_so, ids_si, w_so, w_si = lay
         if pr0c.data_ptr() != pr[0].data_ptr() or (wt is not None and wt0c.data_ptr() != wt[0].data_ptr()) \
                 or (pr.stride(0) * 4) % 16 != 0:
-            for b in range(B):  # layouts that need a copy: go view by view
+            # layouts that need a copy: go view by view. The whole batch may sit in ONE upload buffer: it is released
+            # (may be overwritten by the next upload) only after the last view's kernels, not after the first's.
+            staged, self._stage_last = self._stage_last, None
+            for b in range(B):
                 self.add(ids[b], pr[b], wt[b] if wt is not None else None)
+            self._stage_last = staged
+            self._release_stage()
             return
         npix = n_outer * n_inner
         done = 0
@@ -283,13 +341,18 @@ class MeshAggregator:
         """ModelAggregator::reset (Mesh.h:119-122): every row back to the aggregator's zero (mul: -log 1 = 0)."""
         self._acc.zero_()
 
-    def get(self, device=False):
+    def get(self, device=False, rows=None):
         """Per-primitive class distribution (P, C) (Fusion.h:72-76): the accumulator row (mul: exp(-(l - min l))),
-        L1-normalised, NaN/Inf -> 0. numpy by default like the reference; device=True returns the torch CUDA tensor."""
+        L1-normalised, NaN/Inf -> 0. numpy by default like the reference; device=True returns the torch CUDA tensor.
+        rows=(first, last) (extension): only that slice of primitives."""
         torch = self._torch
-        out = torch.empty((self.primitives, self.classes), dtype=torch.float32, device=self.device)
+        first, last = (0, self.primitives) if rows is None else (int(rows[0]), int(rows[1]))
+        if not (0 <= first <= last <= self.primitives):
+            raise ValueError("get(rows=...): row range outside the primitives")
+        out = torch.empty((last - first, self.classes), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            rc = _lib.lib.smesh_fuse_get(self._kind, self._acc.data_ptr(), self.primitives, self.classes, out.data_ptr(),
+            rc = _lib.lib.smesh_fuse_get(self._kind, self._acc[first:last].data_ptr() if last > first else None, last - first,
+                                         self.classes, out.data_ptr() if last > first else None,
                                          torch.cuda.current_stream().cuda_stream)
         _lib.check(rc)
         return out if device else out.cpu().numpy()
@@ -356,6 +419,22 @@ class MeshAggregator:
         the accumulator of all views added on one GPU up to float reassociation."""
         from .distributed import allreduce_accumulator
         allreduce_accumulator(self._acc, group=group)
+
+    def reduce_scatter_get(self, group=None):
+        """Cheaper end of a view-sharded job when every rank only needs ITS slice of the result: one reduce-scatter (half
+        the bytes of an all-reduce on the wire) leaves rank r with the summed accumulator rows [first, last) of its
+        slice, and get() runs on those rows only. -> ((first, last), distribution rows as a torch CUDA tensor). The
+        local accumulator is left untouched."""
+        from .distributed import reduce_scatter_rows
+        (first, last), part = reduce_scatter_rows(self._acc, group=group)
+        torch = self._torch
+        out = torch.empty((last - first, self.classes), dtype=torch.float32, device=self.device)
+        if last > first:
+            with torch.cuda.device(self.device):
+                rc = _lib.lib.smesh_fuse_get(self._kind, part.data_ptr(), last - first, self.classes, out.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc)
+        return (first, last), out
 
     def state(self):
         """Raw accumulator (P, C) as a torch CUDA tensor (a view without the alignment padding)."""

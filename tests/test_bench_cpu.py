@@ -20,6 +20,7 @@ def test_reference_arm_json_line():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
+    assert line["product_lib_mapped"] is False, "the reference arm must not load libsmesh_b200.so"
 
 
 def test_reference_arm_other_ranks_stay_silent():

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from semantic_meshes import data, synthetic
+from conftest import GOLDEN
 from oracle import write_plain_ply
 
 
@@ -118,3 +119,31 @@ def test_colmap_unsupported_model(tmp_path):
         data.Colmap(str(tmp_path))
     with pytest.raises(IOError, match="could not be found"):
         data.Colmap(str(tmp_path / "nope"))
+
+
+def test_ply_loader_pinned_to_the_genuine_reference_loader():
+    """data.Ply against what the reference's own loader (src/data/Ply.cpp:9-15 + tt/interface/tinyply/Tinyply.h:93-97,
+    195-230 + vendored tinyply, compiled into oracle/_ref/libref_ply.so and run by tests/golden/make_ply_golden.py) makes of
+    the PLY fixtures the reference ships, extern/tinyply/assets/*.ply: the same files load, the same files are rejected
+    (sofa.ply: a face element with more than the list property; elephant.ply: no face element), and a loaded file yields
+    bit-identical float32 vertices and int32 faces (SHA-256 of the arrays)."""
+    import hashlib
+    import json
+    assets = "/root/reference/extern/tinyply/assets"
+    if not os.path.isdir(assets):
+        pytest.skip("reference checkout absent (GPU box)")
+    golden = json.load(open(os.path.join(GOLDEN, "ply_ref.json")))
+    assert sorted(golden) == sorted(f for f in os.listdir(assets) if f.endswith(".ply"))
+    assert sum(1 for g in golden.values() if g["loads"]) >= 4
+    for name, g in golden.items():
+        path = os.path.join(assets, name)
+        if not g["loads"]:
+            with pytest.raises((ValueError, RuntimeError, OSError)):
+                data.Ply(path)
+            continue
+        ply = data.Ply(path)
+        verts = np.ascontiguousarray(ply.vertices, dtype=np.float32)
+        faces = np.ascontiguousarray(ply.faces, dtype=np.int32)
+        assert verts.shape == (g["V"], 3) and faces.shape == (g["F"], 3), name
+        assert hashlib.sha256(verts.tobytes()).hexdigest() == g["verts_sha256"], name
+        assert hashlib.sha256(faces.tobytes()).hexdigest() == g["faces_sha256"], name

@@ -35,7 +35,7 @@ def worker(rank, world, port, kind, out_dir):
         if p not in sys.path:
             sys.path.insert(0, p)
     import oracle
-    from semantic_meshes.distributed import allreduce_accumulator, shard_views
+    from semantic_meshes.distributed import allreduce_accumulator, reduce_scatter_rows, shard_views
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -45,7 +45,10 @@ def worker(rank, world, port, kind, out_dir):
     for v in mine:
         agg.add(*views[v])
     acc = torch.from_numpy(agg.acc)
+    (first, last), part = reduce_scatter_rows(acc)   # rows of this rank's slice, summed over the ranks
     allreduce_accumulator(acc)
+    assert last - first == part.shape[0] and torch.equal(part, acc[first:last])
+    assert (first, last) == ((0, P // 2) if rank == 0 else (P // 2, P))
     np.save(os.path.join(out_dir, f"acc_{kind}_{rank}.npy"), acc.numpy())
     np.save(os.path.join(out_dir, f"views_{kind}_{rank}.npy"), np.array(mine))
     dist.destroy_process_group()

@@ -501,3 +501,263 @@ def test_full_size_properties(sm, shape):
     touched[flat[ok]] = True
     assert torch.allclose(rows[touched], torch.ones_like(rows[touched]), atol=1e-5)
     assert not out[~touched].any().item()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: count stage (cross-column run folding), overlapped batches, token validity, get(), mul fast path, full size
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _count(sm, ids_t, P, epoch=1, want_ids32=False):
+    """smesh_fuse_count through the C ABI on a (W, H) torch tensor of any supported dtype / strides -> counts (P,)"""
+    import torch
+    from semantic_meshes import _lib
+    dt = {torch.uint32: _lib.ID_U32, torch.int32: _lib.ID_I32, torch.uint64: _lib.ID_U64, torch.int64: _lib.ID_I64}[ids_t.dtype]
+    W, H = ids_t.shape
+    counts = torch.zeros(max(P, 1), dtype=torch.int32, device="cuda")
+    ids32 = torch.full((W * H,), 12345, dtype=torch.int32, device="cuda") if want_ids32 else None
+    _lib.check(_lib.lib.smesh_fuse_count(ids_t.data_ptr(), dt, ids_t.stride(0), ids_t.stride(1), W, H, P, counts.data_ptr(), epoch,
+                                         ids32.data_ptr() if want_ids32 else None, torch.cuda.current_stream().cuda_stream))
+    c = counts.cpu().numpy().view(np.uint32)
+    if epoch:
+        assert ((c >> 24 == epoch) | (c == 0)).all()
+        c = c & 0xFFFFFF
+    return c, (ids32.cpu().numpy().view(np.uint32) if want_ids32 else None)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 70), (70, 3), (8, 32), (9, 33), (64, 64), (61, 47), (200, 517), (517, 200)])
+def test_count_stage_exact(sm, shape):
+    """The per-face pixel histogram (Mesh.h:90-93) is exact: blobs of every size (faces spanning several 8-column x
+    32-row blocks, faces split by an occluder so that two runs of one column see the same run of the next), background,
+    out-of-range ids, every id dtype, transposed (strided) index images, tagged and untagged counters."""
+    import torch
+    W, H = shape
+    P = 97
+    rng = np.random.default_rng(W * 131 + H)
+    for block in (1, 2, 3, 5, 16, 40):
+        ids, _ = make_view(rng, W, H, 1, P, block=block, bg=0.15, oob=0.03)
+        if block == 5 and W > 2:
+            ids[1::3] = ids[0]                     # the same column pattern again and again with gaps
+        if block == 3 and H > 8:
+            ids[:, H // 2] = (ids[:, H // 2] + 1) % P   # an occluder line splitting every face in two runs
+        exp = np.bincount(ids[ids < P].astype(np.int64), minlength=P)
+        flat_exp = np.where(ids < P, ids, 0xFFFFFFFF).reshape(-1)
+        t32 = torch.from_numpy(ids.view(np.int32)).cuda()
+        got, _ = _count(sm, t32, P, epoch=1 + block)
+        assert np.array_equal(got, exp), f"block {block}"
+        got, _ = _count(sm, t32, P, epoch=0)
+        assert np.array_equal(got, exp)
+        wide = ids.astype(np.int64)
+        wide[ids == 0xFFFFFFFF] = -1
+        got, flat = _count(sm, torch.from_numpy(wide).cuda(), P, epoch=3, want_ids32=True)
+        assert np.array_equal(got, exp) and np.array_equal(flat, flat_exp)
+        # the transposed view: element (x, y) at y*W + x
+        tr = torch.from_numpy(np.ascontiguousarray(ids.view(np.int32).T)).cuda().t()
+        got, flat = _count(sm, tr, P, epoch=200, want_ids32=True)
+        assert np.array_equal(got, exp) and np.array_equal(flat, flat_exp)
+
+
+def test_count_stage_on_rendered_ids(sm):
+    import torch
+    from semantic_meshes import synthetic
+    W, H = 640, 512
+    mesh = synthetic.mesh("terrain", 60000, seed=5)
+    renderer = sm.render.triangles(mesh)
+    P = renderer.getPrimitivesNum()
+    for cam in synthetic.terrain_cameras(2, W, H, 60000, tris_per_view=25000, seed=12):
+        idx, _ = renderer.render(cam)
+        ids = idx.cpu().numpy().view(np.uint32)
+        got, _ = _count(sm, idx, P, epoch=7)
+        assert np.array_equal(got, np.bincount(ids[ids < P].astype(np.int64), minlength=P))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_add_batch_overlapped_and_captured(sm, kind):
+    """add_batch runs the count stage of view b+1 on a side stream under the scatter stage of view b (two counter arrays):
+    same accumulator as the sequential loop, also with weights, also when the call is captured into a CUDA graph and
+    replayed, and for odd / even batch sizes."""
+    import torch
+    rng = np.random.default_rng(55)
+    W, H, C, P = 96, 130, 19, 400
+    for B in (2, 5, 8):
+        views = [make_view(rng, W, H, C, P, block=1 + (b % 4)) for b in range(B)]
+        ids = torch.from_numpy(np.stack([v[0] for v in views]).view(np.int32)).cuda()
+        probs = torch.from_numpy(np.stack([v[1] for v in views])).cuda()
+        wts = torch.from_numpy((rng.random((B, W, H)) * 2).astype(np.float32)).cuda() if B == 5 else None
+        ref = oracle.Aggregator(P, C, kind)
+        for b, (i, p) in enumerate(views):
+            ref.add(i, p, None if wts is None else wts[b].cpu().numpy())
+        a = sm.fusion.MeshAggregator(P, C, kind)
+        a.add_batch(ids, probs, wts)
+        assert_acc_close(kind, a.state().cpu().numpy(), ref.acc)
+        # captured: every replay adds the batch once more
+        g_agg = sm.fusion.MeshAggregator(P, C, kind)
+        g_agg.restart_epochs()
+        g_agg.add_batch(ids, probs, wts)           # warm-up outside the capture (side stream, kernel attributes)
+        torch.cuda.synchronize()
+        g_agg.reset()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g_agg.restart_epochs()
+            g_agg.add_batch(ids, probs, wts)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert_acc_close(kind, g_agg.state().cpu().numpy(), ref.acc)
+        graph.replay()
+        graph.replay()
+        torch.cuda.synchronize()
+        exp3 = np.where(np.isinf(ref.acc), ref.acc, 3 * ref.acc)
+        assert_acc_close(kind, g_agg.state().cpu().numpy(), exp3, rtol=2e-5)
+
+
+def test_counted_render_token_is_voided_by_later_counts(sm):
+    """render(camera, count_into=agg) leaves the view's counts in one of the aggregator's two counter arrays; the index
+    image may only skip its count pass while that array still holds them. Two plain add() calls (or an add_batch) in
+    between overwrite both arrays: the add of the counted image must then recount - silently using another view's counts
+    would give wrong weights."""
+    import torch
+    from semantic_meshes import synthetic
+    W, H, C = 160, 120, 19
+    mesh = synthetic.mesh("terrain", 6000, seed=2)
+    renderer = sm.render.triangles(mesh)
+    P = renderer.getPrimitivesNum()
+    cams = synthetic.terrain_cameras(3, W, H, 6000, tris_per_view=1500, seed=8)
+    preds = [synthetic.predictions_torch(W, H, C, seed=v, device="cuda") for v in range(3)]
+    plain = [renderer.render(c)[0] for c in cams]
+    for between in ("two_adds", "batch", "nothing"):
+        agg, ref = sm.fusion.MeshAggregator(P, C), sm.fusion.MeshAggregator(P, C)
+        idx0, _ = renderer.render(cams[0], count_into=agg)
+        assert getattr(idx0, "_smesh_counted", None) is not None
+        if between == "two_adds":
+            agg.add(plain[1], preds[1])
+            agg.add(plain[2], preds[2])
+        elif between == "batch":
+            agg.add_batch(torch.stack(plain[1:]), torch.stack(preds[1:]))
+        agg.add(idx0, preds[0])
+        if between != "nothing":
+            ref.add(plain[1], preds[1])
+            ref.add(plain[2], preds[2])
+        ref.add(plain[0], preds[0])
+        torch.testing.assert_close(agg.state(), ref.state(), rtol=1e-5, atol=1e-7)
+
+
+def test_fused_count_pipeline_across_epoch_wrap(sm):
+    """ViewPipeline(fused_count=True) over more than 255 views: the 8-bit count epoch wraps inside the run, the counters
+    are zeroed on the render stream and both streams are ordered around that reset."""
+    import torch
+    from semantic_meshes import synthetic
+    from semantic_meshes.pipeline import ViewPipeline
+    W, H, C = 96, 80, 19
+    mesh = synthetic.mesh("terrain", 4000, seed=4)
+    renderer = sm.render.triangles(mesh)
+    P = renderer.getPrimitivesNum()
+    base = synthetic.terrain_cameras(6, W, H, 4000, tris_per_view=1200, seed=3)
+    n = 600
+    cams = [base[v % 6] for v in range(n)]
+    preds6 = torch.stack([synthetic.predictions_torch(W, H, C, seed=v, device="cuda") for v in range(6)])
+    preds = [preds6[v % 6] for v in range(n)]
+    seq = sm.fusion.MeshAggregator(P, C)
+    for v in range(6):
+        idx, _ = renderer.render(base[v])
+        seq.add(idx, preds6[v])
+    ovl = sm.fusion.MeshAggregator(P, C)
+    ViewPipeline(renderer, ovl, fused_count=True).run(cams, preds)
+    torch.cuda.synchronize()
+    assert torch.isfinite(ovl.state()).all()
+    torch.testing.assert_close(ovl.state(), (n // 6) * seq.state(), rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("C", [1, 3, 19, 40, 150, 700, 3000])
+def test_get_kernel_shapes(sm, kind, C):
+    """get(): rows staged through shared memory in blocks of 256 (fewer for wide class vectors, one thread per row straight
+    from global memory beyond ~1500 classes), block boundaries at P = 1, 255, 256, 257, 1000; untouched rows, +inf entries
+    (mul) and huge / tiny magnitudes; against the oracle's get() on the same raw accumulator."""
+    rng = np.random.default_rng(C)
+    for P in (1, 255, 256, 257, 1000):
+        acc = np.abs(rng.normal(size=(P, C))).astype(np.float32) * np.float32(10.0) ** rng.integers(-3, 4, size=(P, 1)).astype(np.float32)
+        acc[rng.random(P) < 0.2] = 0                      # faces never seen
+        if kind == "mul":
+            acc[rng.random((P, C)) < 0.05] = np.inf       # absorbing zero probability
+            if P > 3:
+                acc[3] = np.inf                            # every class impossible
+        agg, ref = sm.fusion.MeshAggregator(P, C, kind), oracle.Aggregator(P, C, kind)
+        agg.load_state(acc)
+        ref.acc[...] = acc
+        got = agg.get()
+        assert got.shape == (P, C) and np.isfinite(got).all()
+        assert_get_close(kind, got, ref.get())
+
+
+def test_mul_direct_form_matches_reference_sequence(sm, monkeypatch):
+    """mul accumulates -log(p^w). The kernels use -w log p where p^w stays a normal float and the reference's own
+    powf + logf sequence elsewhere (underflow to the absorbing zero, p = 0, w = 0); SMESH_MUL_EXACT=1 forces the reference's
+    sequence for every element. Both against the oracle and against each other, with probabilities down to 1e-38, weights
+    from 0 to 40 and exact zeros."""
+    import torch
+    rng = np.random.default_rng(8)
+    W, H, P = 64, 48, 150
+    for C in (19, 40, 150):
+        ids, probs = make_view(rng, W, H, C, P, block=2)
+        tiny = rng.random((W, H, C)) < 0.03
+        probs[tiny] = np.float32(10.0) ** rng.uniform(-38, -5, size=int(tiny.sum())).astype(np.float32)
+        wts = (rng.random((W, H)) * np.where(rng.random((W, H)) < 0.1, 40.0, 2.0)).astype(np.float32)
+        wts[rng.random((W, H)) < 0.05] = 0
+        ref = oracle.Aggregator(P, C, "mul")
+        ref.add(ids, probs, wts)
+        states = []
+        for exact in ("0", "1"):
+            monkeypatch.setenv("SMESH_MUL_EXACT", exact)
+            agg = sm.fusion.MeshAggregator(P, C, "mul")
+            agg.add(ids, probs, wts)
+            states.append(agg.state().cpu().numpy())
+            assert_acc_close("mul", states[-1], ref.acc)
+            assert_get_close("mul", agg.get(), ref.get())
+        assert np.isinf(ref.acc).any()
+        assert np.array_equal(np.isinf(states[0]), np.isinf(states[1]))
+
+
+def test_summax_runs_of_equal_class_merge(sm):
+    """summax folds consecutive pixels of one face with the same best class into one reduction: piecewise-constant
+    predictions (long runs), ties between classes (first maximum wins), class changes inside a face."""
+    import torch
+    rng = np.random.default_rng(4)
+    W, H, C, P = 40, 200, 19, 60
+    ids, probs = make_view(rng, W, H, C, P, block=8)
+    blocky = probs[::4, ::10].repeat(4, 0).repeat(10, 1)[:W, :H].copy()
+    blocky[5:9, 20:60, 3] = blocky[5:9, 20:60].max(-1)     # ties: class 3 equals the maximum
+    agg, ref = sm.fusion.MeshAggregator(P, C, "summax"), oracle.Aggregator(P, C, "summax")
+    for pr in (blocky, probs):
+        agg.add(ids, pr)
+        ref.add(ids, pr)
+    assert_acc_close("summax", agg.state().cpu().numpy(), ref.acc)
+
+
+@pytest.mark.parametrize("name,kinds", [("cfg3", KINDS), ("cfg5", ["sum"])])
+def test_full_size_against_genuine_reference_aggregator(sm, name, kinds):
+    """FULL-SIZE views (config 3: 2 M faces, 2048x1024x19; config 5: 5 M faces, 1280x720x19) rendered by our rasterizer and
+    fused by the GENUINE reference aggregator (oracle/_ref/libref_fusion.so, all host threads) and by ours, all three
+    aggregator kinds at config 3: get() within 1e-5 (mul: 5e-4, the reference's own run-to-run spread after exp)."""
+    import torch
+    import bench
+    from semantic_meshes import synthetic
+    if not (os.path.exists(oracle.ref_fusion_path()) and oracle.ref_fusion_lib().ref_fusion_has_classes(19)):
+        pytest.skip("genuine reference aggregator build absent")
+    cfg = bench.CONFIGS[name]
+    W, H, C = cfg["W"], cfg["H"], cfg["C"]
+    mesh, cams = bench.build_scene(cfg, 0, 2)
+    renderer = sm.render.triangles(mesh)
+    P = renderer.getPrimitivesNum()
+    views = []
+    for v, cam in enumerate(cams):
+        idx, _ = renderer.render(cam)
+        views.append((idx, synthetic.predictions_torch(W, H, C, seed=900 + v, device="cuda")))
+    host = [(i.cpu().numpy().view(np.uint32), p.cpu().numpy()) for i, p in views]
+    for kind in kinds:
+        ours, ref = sm.fusion.MeshAggregator(P, C, kind), oracle.RefAggregator(P, C, kind)
+        for (i, p), (hi, hp) in zip(views, host):
+            ours.add(i, p)
+            ref.add(hi, hp)
+        got, exp = ours.get(), ref.get()
+        ref.close()
+        assert (exp.sum(-1) > 0.5).sum() > 100000
+        assert_get_close(kind, got, exp)
