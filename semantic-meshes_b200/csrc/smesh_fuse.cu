@@ -164,7 +164,7 @@ __device__ __forceinline__ uint32_t sanitize_id(int64_t raw, int64_t P)
   return (raw >= 0 && raw < P) ? (uint32_t) raw : INVALID_ID;
 }
 
-// Variant A (SMESH_COUNT_VARIANT=0): flat order, 4 independent 32-pixel groups per warp iteration, runs of equal ids inside
+// Variant A (SMESH_COUNT_VARIANT=0, the default): flat order, 4 independent 32-pixel groups per warp iteration, runs of equal ids inside
 // a group merged by ballot into one pair of reductions.
 constexpr int COUNT_UNROLL = 4; // independent 32-pixel groups per warp iteration (loads in flight per lane)
 
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256) count_runs_kernel(const IdT* __restrict__
   }
 }
 
-// Variant B (default): a warp counts a BLOCK of the image: COLS consecutive outer indices (image columns) x 32 consecutive
+// Variant B (SMESH_COUNT_VARIANT=1..3, measured slower, kept for the record): a warp counts a BLOCK of the image: COLS consecutive outer indices (image columns) x 32 consecutive
 // inner ones (rows), lane = row. Inside a column, runs of equal ids are found by ballot (one length per run head). A face
 // covers a few adjacent columns at overlapping rows, so the run of a face in column k+1 is then folded into its run in
 // column k (right to left, lengths travel by shuffle): one pair of reductions per face and block instead of one per
@@ -333,6 +333,41 @@ __global__ void __launch_bounds__(256) count_kernel(const IdT* __restrict__ ids,
   }
 }
 
+// The count stage (flat uint32 ids, tagged counters) as a job of ONE warp of a persistent CTA: the CTA's share of the
+// image in chunks of COUNT_UNROLL x 32 pixels, runs inside a 32-pixel group merged into one pair of reductions.
+__device__ __forceinline__ void count_job_warp(const uint32_t* __restrict__ ids, int64_t npix, uint32_t P32,
+                                               uint32_t* __restrict__ counts, uint32_t tag, int lane)
+{
+  for (int64_t base = (int64_t) blockIdx.x * (32 * COUNT_UNROLL); base < npix; base += (int64_t) gridDim.x * (32 * COUNT_UNROLL))
+  {
+    uint32_t id[COUNT_UNROLL];
+#pragma unroll
+    for (int k = 0; k < COUNT_UNROLL; k++)
+    {
+      const int64_t i = base + k * 32 + lane;
+      id[k] = i < npix ? __ldg(ids + i) : INVALID_ID;
+      if (!(id[k] < P32))
+      {
+        id[k] = INVALID_ID;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < COUNT_UNROLL; k++)
+    {
+      const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, id[k], 1);
+      const bool head = (lane == 0) || (prev != id[k]);
+      const uint32_t headmask = __ballot_sync(0xFFFFFFFFu, head);
+      if (head && id[k] != INVALID_ID)
+      {
+        const uint32_t above = headmask & ~((2u << lane) - 1u);
+        const int next = above ? (__ffs(above) - 1) : 32;
+        atomicMax(counts + id[k], tag);
+        atomicAdd(counts + id[k], (uint32_t) (next - lane));
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) clear_kernel(const uint32_t* __restrict__ ids32, int64_t npix, int64_t P,
                                                     uint32_t* __restrict__ counts)
 {
@@ -366,6 +401,12 @@ struct ScatterArgs
   uint32_t count_mask;     // COUNT_MASK with a tagged epoch, 0xFFFFFFFF without
   uint32_t run_cap;        // power of two <= 32: runs of equal ids are cut every run_cap lanes
   int mul_exact;           // mul: the reference's powf + logf sequence for every element (see neg_log_pow)
+  // Optional second job of the ring kernels: the count stage of the NEXT view of a batch (smesh_fuse_add_batch), done by
+  // one extra warp per CTA while the consumer warps scatter this view. NULL = none.
+  const uint32_t* next_ids;   // [next_npix] flat uint32 ids of the next view
+  uint32_t* next_counts;      // [P] the OTHER counter array
+  int64_t next_npix;
+  uint32_t next_tag;          // its epoch << COUNT_BITS (tagged counters only)
 
   float iew;
 };
@@ -407,13 +448,14 @@ __device__ __forceinline__ void load_chunk(const float* __restrict__ p, int nval
 
 // Shared memory: [stages][NW*32*C] floats | full[stages], empty[stages] mbarriers
 template <int KIND, int CT>
-__global__ void __launch_bounds__(288) scatter_kernel(ScatterArgs a)
+__global__ void __launch_bounds__(320) scatter_kernel(ScatterArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int C = CT > 0 ? CT : a.C;
   const int Cpad = CT > 0 ? ((CT + 3) & ~3) : a.Cpad;
   const int al = (C % 4 == 0) ? 4 : ((C % 2 == 0) ? 2 : 1);
-  const int NW = (int) (blockDim.x >> 5) - 1; // consumer warps; warp 0 produces
+  const bool has_count = a.next_ids != nullptr;
+  const int NW = (int) (blockDim.x >> 5) - 1 - (has_count ? 1 : 0); // consumer warps; warp 0 produces, the last one may count
   const int tile_px = NW * 32;
   const size_t stage_floats = (size_t) tile_px * C;
   const int stages = a.stages;
@@ -474,6 +516,13 @@ __global__ void __launch_bounds__(288) scatter_kernel(ScatterArgs a)
         }
       }
     }
+    return;
+  }
+
+  if (warp == NW + 1)
+  {
+    // ===== the next view's count stage (smesh_fuse_add_batch) =====
+    count_job_warp(a.next_ids, a.next_npix, (uint32_t) a.P, a.next_counts, a.next_tag, lane);
     return;
   }
 
@@ -689,14 +738,15 @@ __global__ void __launch_bounds__(288) scatter_kernel(ScatterArgs a)
 // LEAN: compiled for 8 CTAs of <= 3 consumer warps per SM (64 registers instead of 84, 24 bytes of spills): leaves room
 // for more rasterizer CTAs next to it. Opt-in (SMESH_PAIR_LEAN=1, C = 19), not measured yet.
 template <int KIND, int CT, bool LEAN = false>
-__global__ void __launch_bounds__(LEAN ? 128 : 288, LEAN ? 8 : 0) scatter_pair_kernel(ScatterArgs a)
+__global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LEAN ? 64 : 88) scatter_pair_kernel(ScatterArgs a)
 {
   static_assert(CT >= 1 && CT <= CH, "pair kernel holds 2 x Cpad values in registers");
   constexpr int C = CT;
   constexpr int Cpad = (CT + 3) & ~3;
   constexpr int NCHUNK = Cpad / 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int NW = (int) (blockDim.x >> 5) - 1;
+  const bool has_count = a.next_ids != nullptr;
+  const int NW = (int) (blockDim.x >> 5) - 1 - (has_count ? 1 : 0); // consumer warps (warp 0 produces, the last may count)
   const int tile_px = NW * 64;
   const size_t stage_floats = (size_t) tile_px * C;
   const int stages = a.stages;
@@ -756,6 +806,13 @@ __global__ void __launch_bounds__(LEAN ? 128 : 288, LEAN ? 8 : 0) scatter_pair_k
         }
       }
     }
+    return;
+  }
+
+  if (warp == NW + 1)
+  {
+    // ===== the next view's count stage (smesh_fuse_add_batch): hidden under this view's scatter =====
+    count_job_warp(a.next_ids, a.next_npix, (uint32_t) a.P, a.next_counts, a.next_tag, lane);
     return;
   }
 
@@ -1489,7 +1546,7 @@ static int launch_scatter_ring(const ScatterArgs& args_in, const RingConfig& cfg
   ScatterArgs args = args_in;
   const size_t smem = ring_smem_bytes(args.C, cfg);
   auto kernel = scatter_kernel<KIND, CT>;
-  const int threads = (cfg.consumer_warps + 1) * 32;
+  const int threads = (cfg.consumer_warps + 1 + (args.next_ids != nullptr ? 1 : 0)) * 32;
   int blocks_per_sm = 0;
   const int cfg_rc = kernel_blocks_per_sm(reinterpret_cast<const void*>(kernel), threads, smem, &blocks_per_sm);
   if (cfg_rc != SMESH_OK)
@@ -1549,7 +1606,7 @@ static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
   const size_t smem = (size_t) cfg.stages * cfg.consumer_warps * 64 * CT * 4 + (size_t) cfg.stages * 16 +
                       (size_t) cfg.consumer_warps * (64 * ((CT + 3) & ~3) + 64) * 4; // flush rows + their face ids
   auto kernel = scatter_pair_kernel<KIND, CT, LEAN>;
-  const int threads = (cfg.consumer_warps + 1) * 32;
+  const int threads = (cfg.consumer_warps + 1 + (args.next_ids != nullptr ? 1 : 0)) * 32;
   int blocks_per_sm = 0;
   const int cfg_rc = kernel_blocks_per_sm(reinterpret_cast<const void*>(kernel), threads, smem, &blocks_per_sm);
   if (cfg_rc != SMESH_OK)
@@ -1572,6 +1629,9 @@ static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
   SMESH_LAUNCH_CHECK("scatter_pair_kernel");
   return SMESH_OK;
 }
+
+// Can the scatter launch of these arguments carry the next view's count stage? (the two ring kernels can)
+static bool scatter_takes_count_job(int kind, const ScatterArgs& args);
 
 template <int KIND>
 static int launch_scatter(const ScatterArgs& args, cudaStream_t stream)
@@ -1622,12 +1682,15 @@ static int launch_scatter(const ScatterArgs& args, cudaStream_t stream)
   return SMESH_OK;
 }
 
-// SMESH_COUNT_VARIANT (tuning / profiling): 0 = flat runs; 1 = blocks of 8 columns (default); 2 = 4 columns; 3 = 2 columns;
-// 10 / 11 = variants 0 / 1 without their reductions (the floor of the id traffic and the bookkeeping)
+// SMESH_COUNT_VARIANT (tuning / profiling): 0 = flat runs (default); 1 / 2 / 3 = blocks of 8 / 4 / 2 columns with runs folded
+// across columns; 10 / 11 = variants 0 / 1 without their reductions (the floor of the id traffic and the bookkeeping).
+// Measured on cfg3 (profiles/r02b_count_variants.txt): folding halves the reductions (1.38 M -> 0.64 M L2 sectors) but
+// doubles the instructions and is slower (11.3 vs 8.3 us): the stage is bound by launch + load latency (5.4 us without
+// any reduction), not by the reductions.
 static int count_variant()
 {
   const char* e = getenv("SMESH_COUNT_VARIANT");
-  return e ? atoi(e) : 1;
+  return e ? atoi(e) : 0;
 }
 
 template <typename IdT>
@@ -1713,7 +1776,23 @@ static ScatterArgs make_scatter_args(const uint32_t* ids32, const float* probs, 
   const char* mul_exact_env = getenv("SMESH_MUL_EXACT"); // read per call: tests switch it
   args.mul_exact = (mul_exact_env != nullptr && atoi(mul_exact_env) != 0) ? 1 : 0;
   args.iew = iew;
+  args.next_ids = nullptr;
+  args.next_counts = nullptr;
+  args.next_npix = 0;
+  args.next_tag = 0;
   return args;
+}
+
+static bool scatter_takes_count_job(int kind, const ScatterArgs& args)
+{
+  // mirrors launch_scatter(): class-parallel kernel for wide C (no spare warp), else a ring kernel if the image is aligned
+  int vw = 1;
+  RingConfig cfg;
+  if (kind != SMESH_KIND_SUMMAX && rows_kernel_takes(args, vw))
+  {
+    return false;
+  }
+  return (reinterpret_cast<uintptr_t>(args.probs) & 15) == 0 && ring_config(args.C, cfg);
 }
 
 static int launch_scatter_kind(int kind, const ScatterArgs& args, cudaStream_t stream)
@@ -1750,10 +1829,19 @@ struct ViewStages
                             zero_copy ? nullptr : ids32, epoch, stream);
   }
 
-  int scatter(uint32_t* counts, uint32_t epoch, cudaStream_t stream) const
+  // next / next_counts / next_epoch: the view whose count stage rides along (NULL = none); see ScatterArgs
+  int scatter(uint32_t* counts, uint32_t epoch, cudaStream_t stream, const ViewStages* next = nullptr,
+              uint32_t* next_counts = nullptr, uint32_t next_epoch = 0) const
   {
-    const int rc = launch_scatter_kind(kind, make_scatter_args(flat_ids(), probs, weights, counts, acc, npix(), C, P, iew, epoch),
-                                       stream);
+    ScatterArgs args = make_scatter_args(flat_ids(), probs, weights, counts, acc, npix(), C, P, iew, epoch);
+    if (next != nullptr)
+    {
+      args.next_ids = next->flat_ids();
+      args.next_counts = next_counts;
+      args.next_npix = next->npix();
+      args.next_tag = next_epoch << COUNT_BITS;
+    }
+    const int rc = launch_scatter_kind(kind, args, stream);
     if (rc != SMESH_OK)
     {
       return rc;
@@ -1811,47 +1899,6 @@ static int add_view(int kind, const void* ids, int id_dtype, int64_t ids_so, int
   }
   rc = v.count(counts, epoch, stream);
   return rc != SMESH_OK ? rc : v.scatter(counts, epoch, stream);
-}
-
-// Side stream of smesh_fuse_add_batch (one per host thread and device, created on first use and kept): the count stage
-// of view b+1 runs on it while the scatter stage of view b runs on the caller's stream. Fork and join are event waits,
-// so the pattern is also legal inside a stream capture (the side stream joins the capture and leaves it again).
-struct SideStream
-{
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr;
-  cudaEvent_t counted[2] = {nullptr, nullptr};
-  cudaEvent_t scattered[2] = {nullptr, nullptr};
-};
-
-static int side_stream(SideStream** out)
-{
-  constexpr int MAX_DEVICES = 64;
-  static thread_local SideStream table[MAX_DEVICES];
-  int device = 0;
-  SMESH_CUDA_CHECK(cudaGetDevice(&device));
-  if (device < 0 || device >= MAX_DEVICES)
-  {
-    *out = nullptr;
-    return SMESH_OK;
-  }
-  SideStream& s = table[device];
-  if (s.stream == nullptr)
-  {
-    // lowest priority: when a scatter launch and the next view's count launch are ready together, the scatter CTAs go
-    // first and the count CTAs fill what is left of the SMs
-    int least = 0, greatest = 0;
-    SMESH_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    SMESH_CUDA_CHECK(cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, least));
-    SMESH_CUDA_CHECK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
-    for (int i = 0; i < 2; i++)
-    {
-      SMESH_CUDA_CHECK(cudaEventCreateWithFlags(&s.counted[i], cudaEventDisableTiming));
-      SMESH_CUDA_CHECK(cudaEventCreateWithFlags(&s.scattered[i], cudaEventDisableTiming));
-    }
-  }
-  *out = &s;
-  return SMESH_OK;
 }
 
 static int check_add_args(const char* fn, int kind, const void* ids, const float* probs, int64_t n_outer, int64_t n_inner,
@@ -2002,48 +2049,11 @@ extern "C" int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id
   auto epoch_of = [&](int64_t b) -> uint32_t { return count_epoch0 != 0 ? count_epoch0 + (uint32_t) b : 0u; };
   auto counts_of = [&](int64_t b) -> uint32_t* { return counts2 + (size_t) (epoch_of(b) & 1u) * (size_t) P; };
 
-  ViewStages v0;
-  rc = view(0, v0);
-  if (rc != SMESH_OK)
-  {
-    return rc;
-  }
   static const bool no_overlap = getenv("SMESH_NO_BATCH_OVERLAP") != nullptr; // profiling only
-  SideStream* side = nullptr;
-  // overlap needs tagged counters (two arrays in flight) and ids that are consumed in place (one ids32 scratch)
-  if (B >= 2 && count_epoch0 != 0 && v0.zero_copy && !no_overlap)
-  {
-    rc = side_stream(&side);
-    if (rc != SMESH_OK)
-    {
-      return rc;
-    }
-  }
-  if (side == nullptr)
-  {
-    for (int64_t b = 0; b < B; b++)
-    {
-      ViewStages v;
-      rc = view(b, v);
-      if (rc == SMESH_OK) rc = v.count(counts_of(b), epoch_of(b), stream);
-      if (rc == SMESH_OK) rc = v.scatter(counts_of(b), epoch_of(b), stream);
-      if (rc != SMESH_OK)
-      {
-        return rc;
-      }
-    }
-    return SMESH_OK;
-  }
-  // count(b + 1) on the side stream under scatter(b) on the caller's stream. count(b + 1) writes the array scatter(b - 1)
-  // read, so it waits for that scatter; scatter(b + 1) waits for count(b + 1). The last event the caller's stream waits
-  // for is the side stream's last operation: the side stream has joined when the call returns.
-  SMESH_CUDA_CHECK(cudaEventRecord(side->fork, stream));
-  SMESH_CUDA_CHECK(cudaStreamWaitEvent(side->stream, side->fork, 0));
-  rc = v0.count(counts_of(0), epoch_of(0), stream);
-  if (rc != SMESH_OK)
-  {
-    return rc;
-  }
+  // The count stage of view b+1 rides in the scatter launch of view b (one extra warp per CTA of the ring kernels, see
+  // ScatterArgs): it needs tagged counters (two arrays in flight), ids that are consumed in place (no ids32 scratch) and a
+  // scatter kernel with a spare warp. Otherwise the stages simply alternate.
+  bool counted = false; // view b's counts are already in flight
   for (int64_t b = 0; b < B; b++)
   {
     ViewStages v, vn;
@@ -2052,37 +2062,33 @@ extern "C" int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id
     {
       return rc;
     }
-    if (b + 1 < B)
+    if (!counted)
+    {
+      rc = v.count(counts_of(b), epoch_of(b), stream);
+      if (rc != SMESH_OK)
+      {
+        return rc;
+      }
+    }
+    bool carry = false;
+    if (b + 1 < B && count_epoch0 != 0 && !no_overlap)
     {
       rc = view(b + 1, vn);
       if (rc != SMESH_OK)
       {
         return rc;
       }
-      if (b >= 1)
-      {
-        SMESH_CUDA_CHECK(cudaStreamWaitEvent(side->stream, side->scattered[(b - 1) & 1], 0));
-      }
-      rc = vn.count(counts_of(b + 1), epoch_of(b + 1), side->stream);
-      if (rc != SMESH_OK)
-      {
-        return rc;
-      }
-      SMESH_CUDA_CHECK(cudaEventRecord(side->counted[(b + 1) & 1], side->stream));
+      carry = vn.zero_copy && v.zero_copy &&
+              scatter_takes_count_job(kind, make_scatter_args(v.flat_ids(), v.probs, v.weights, counts_of(b), acc, v.npix(), C, P,
+                                                              iew, epoch_of(b)));
     }
-    if (b >= 1)
-    {
-      SMESH_CUDA_CHECK(cudaStreamWaitEvent(stream, side->counted[b & 1], 0));
-    }
-    rc = v.scatter(counts_of(b), epoch_of(b), stream);
+    rc = carry ? v.scatter(counts_of(b), epoch_of(b), stream, &vn, counts_of(b + 1), epoch_of(b + 1))
+               : v.scatter(counts_of(b), epoch_of(b), stream);
     if (rc != SMESH_OK)
     {
       return rc;
     }
-    if (b + 2 < B)
-    {
-      SMESH_CUDA_CHECK(cudaEventRecord(side->scattered[b & 1], stream));
-    }
+    counted = carry;
   }
   return SMESH_OK;
 }

@@ -44,6 +44,8 @@ for variant in (0, 1, 2, 3, 10, 11):
         ref = c
     elif variant < 10:
         assert torch.equal(c, ref), f"variant {variant} counts differ"
+    if os.environ.get("NCU") == "1":  # under ncu: the eager launches above are all that is needed
+        continue
     t_count = bench.timed_graph(torch, count_all, 10) / B * 1e3
     line = f"variant {variant:2d}: count {t_count:6.2f} us"
     if variant < 10:
