@@ -67,10 +67,12 @@ const char* smesh_version(void);
 
 /*
  * Prepared mesh. smesh_raster_mesh_build turns the arrays TriangleRenderer's ctor uploads (TriangleRenderer.h:30-39) into
- * one device blob, once per mesh: vertices repacked as float4, faces sorted along a Morton curve of their centroids and
- * cut into clusters of 128 with a bounding sphere each (a view skips the clusters that are provably behind the camera or
- * far outside the image), every face tagged "well shaped" (sine of the smallest angle >= 0.1) or not. The index image
- * still reports ORIGINAL face indices. Results do not depend on the order of the faces.
+ * one device blob, once per mesh: faces sorted along a Morton curve of their centroids and cut into units of 32 (one per
+ * lane of a warp); a unit is ONE contiguous 1536-byte block holding, per face, its three vertices and its original index
+ * (a view fetches it with a single bulk copy, no index -> vertex gathers), with a bounding sphere (a view skips the units
+ * that are provably behind the camera or far outside the image); every face is tagged "well shaped" (sine of the smallest
+ * angle >= 0.1) or not. 48 bytes per face. The index image still reports ORIGINAL face indices. Results do not depend on
+ * the order of the faces.
  *   verts   float32[V][3], faces int32[F][3] with 0 <= index < V   (F < 2^32 - 1, V < 2^31)
  *   mesh_out / temp   256-byte aligned device buffers of the sizes smesh_raster_mesh_bytes reports; temp is scratch for
  *           the build only (sort keys), mesh_out is what smesh_raster_render takes

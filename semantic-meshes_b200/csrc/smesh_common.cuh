@@ -42,4 +42,76 @@ static inline size_t align_up(size_t v, size_t a)
   return (v + a - 1) / a * a;
 }
 
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX helpers (mbarrier + bulk async copy = the non-tensor TMA path, SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+  return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "SMESH_WAIT_%=:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+    "@p bra SMESH_DONE_%=;\n"
+    "bra SMESH_WAIT_%=;\n"
+    "SMESH_DONE_%=:\n"
+    "}\n" ::"r"(smem_u32(bar)),
+    "r"(parity), "r"(0x989680u) // suspend-time hint: the thread sleeps in hardware until the phase completes instead of
+                                // coming back to poll (the polling of 592 producers was 5 M warp instructions per view)
+    : "memory");
+}
+
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  return policy;
+}
+
+// global -> shared bulk copy, completion signalled on an mbarrier; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                 smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+
+// the same without a cache policy (data that should stay in L2)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) accesses
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+#endif // __CUDACC__
+
 } // namespace smesh

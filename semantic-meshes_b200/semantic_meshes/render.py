@@ -28,8 +28,8 @@ class TriangleRenderer:
         if faces.size and (faces.min() < 0 or faces.max() >= verts.shape[0]):
             raise ValueError("render.triangles: face index out of range")
         self._V, self._F = int(verts.shape[0]), int(faces.shape[0])
-        # what TriangleRenderer's ctor uploads (TriangleRenderer.h:30-39), turned into the prepared mesh once: float4
-        # vertices, Morton-sorted faces in clusters of 128 with bounding spheres (include/smesh.h)
+        # what TriangleRenderer's ctor uploads (TriangleRenderer.h:30-39), turned into the prepared mesh once:
+        # Morton-sorted faces in units of 32, each one contiguous block of vertices + a bounding sphere (include/smesh.h)
         mesh_bytes, temp_bytes = ctypes.c_size_t(0), ctypes.c_size_t(0)
         _lib.check(_lib.lib.smesh_raster_mesh_bytes(self._V, self._F, ctypes.byref(mesh_bytes), ctypes.byref(temp_bytes)))
         with torch.cuda.device(self.device):
@@ -50,13 +50,13 @@ class TriangleRenderer:
     def face_flags(self):
         """Diagnostics: uint8 numpy (F,), 1 where the prepared mesh tagged the face "well shaped" (include/smesh.h)."""
         import numpy as np
-        V, F = self._V, self._F
-        nc = (F + 127) // 128
-        off = ((max(V, 1) * 16 + 255) // 256) * 256
-        rec = self._mesh[off:off + nc * 128 * 16].view(self._torch.int32).view(-1, 4).cpu().numpy()
+        F = self._F
+        nu = (F + 31) // 32
+        # unit blocks come first in the prepared mesh: per face 3 float4 {v0, index bits}, {v1, flags}, {v2, 0}
+        rec = self._mesh[:nu * 32 * 48].view(self._torch.int32).view(-1, 12).cpu().numpy()
         rec = rec[rec[:, 3] != -1]
         out = np.zeros(F, dtype=np.uint8)
-        out[rec[:, 3].astype(np.int64)] = (rec[:, 0] < 0).astype(np.uint8)
+        out[rec[:, 3].astype(np.int64)] = (rec[:, 7] & 1).astype(np.uint8)
         return out
 
     def _ensure_workspace(self, W, H):
