@@ -342,6 +342,15 @@ def stage_timings(args, scene, agg, use_graph, kinds=("sum",), with_get=True):
     if with_get:
         out["get_ms"] = timed_graph(torch, lambda: agg.get(device=True), 5, use_graph)
         out["get_roofline_frac"] = (4.0 * P * (agg._cpad + C)) / (out["get_ms"] * 1e-3) / 1e9 / measured_peak_gbs()[0]
+    if with_get:
+        # render.texels: host constructor (OpenMP over the triangles, like the reference's) + per-view render
+        t0 = time.perf_counter()
+        tex = semantic_meshes.render.texels(scene.mesh, scene.cams, 0.1)
+        out["texels_prepare_s"] = time.perf_counter() - t0
+        out["texels_primitives"] = tex.getPrimitivesNum()
+        out["texels_render_ms_per_view"] = timed_graph(torch, lambda: [tex.render(scene.cams[b]) for b in range(B)], 5,
+                                                       use_graph) / B
+        del tex
     out["render_views_per_s"] = 1e3 / out["render_ms_per_view"]
     out["add_views_per_s"] = 1e3 / out["add_ms_per_view"]
     return out

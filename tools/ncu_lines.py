@@ -13,11 +13,23 @@ for i, l in enumerate(lines):
         blocks.append(cur)
     elif cur is not None and not l.startswith('"File Path"'):
         cur["rows"].append(l)
-seen = set()
+# a kernel has one block per source FILE it inlines code from: report the one with the most instructions
+best = None
 for b in blocks:
-    if want not in b["name"] or b["name"] in seen:
+    if want not in b["name"]:
         continue
-    seen.add(b["name"])
+    rd0 = csv.reader(io.StringIO("\n".join(b["rows"])))
+    h0 = next(rd0)
+    k0 = h0.index("Instructions Executed")
+    n0 = 0
+    for r in rd0:
+        try:
+            n0 += int(r[k0])
+        except (ValueError, IndexError):
+            pass
+    if best is None or n0 > best[0]:
+        best = (n0, b)
+for b in ([best[1]] if best else []):
     rd = csv.reader(io.StringIO("\n".join(b["rows"])))
     hdr = next(rd)
     iline, isrc = 0, 1
