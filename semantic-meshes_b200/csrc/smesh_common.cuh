@@ -112,19 +112,6 @@ __device__ __forceinline__ void fence_proxy_async_smem()
 {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// Programmatic dependent launch (PTX griddepcontrol): a kernel launched with the programmatic-stream-serialization
-// attribute may start while its predecessor in the stream is still running, once every CTA of the predecessor has called
-// grid_launch_dependents() (or exited); it must call grid_dependency_wait() before it touches anything the predecessor
-// writes. Both are no-ops in launches without the attribute / without a dependent.
-__device__ __forceinline__ void grid_launch_dependents()
-{
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-
-__device__ __forceinline__ void grid_dependency_wait()
-{
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
 #endif // __CUDACC__
 
 } // namespace smesh

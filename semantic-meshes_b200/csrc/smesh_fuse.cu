@@ -117,7 +117,6 @@ __global__ void __launch_bounds__(256) count_runs_kernel(const IdT* __restrict__
                                                          int64_t n_inner, int64_t npix, int64_t P, uint32_t* __restrict__ counts,
                                                          uint32_t* __restrict__ ids32, int flat, uint32_t epoch)
 {
-  grid_launch_dependents(); // the scatter launch that follows may set itself up (ring, first tiles, ids) under this kernel
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
@@ -352,8 +351,6 @@ struct ScatterArgs
   uint32_t* next_counts;      // [P] the OTHER counter array
   int64_t next_npix;
   uint32_t next_tag;          // its epoch << COUNT_BITS (tagged counters only)
-  int pdl;                    // host only: launch with programmatic stream serialization (the launch before it on the
-                              // stream is the count stage or the previous view's scatter of the same batch)
 
   float iew;
 };
@@ -423,7 +420,6 @@ __global__ void __launch_bounds__(320) scatter_kernel(ScatterArgs a)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  grid_launch_dependents(); // the next view's scatter of a batch may start filling its ring as CTAs of this one retire
 
   if (warp == 0)
   {
@@ -470,8 +466,6 @@ __global__ void __launch_bounds__(320) scatter_kernel(ScatterArgs a)
   if (warp == NW + 1)
   {
     // ===== the next view's count stage (smesh_fuse_add_batch) =====
-    // (the array it writes is the one the PREVIOUS view's scatter reads: that launch must be over, not just started)
-    grid_dependency_wait();
     count_job_warp(a.next_ids, a.next_npix, (uint32_t) a.P, a.next_counts, a.next_tag, lane);
     return;
   }
@@ -499,7 +493,6 @@ __global__ void __launch_bounds__(320) scatter_kernel(ScatterArgs a)
   int64_t tile = blockIdx.x;
   uint32_t id = load_id(tile), id1 = load_id(tile + tile_stride);
   float wt = load_wt(tile), wt1 = load_wt(tile + tile_stride);
-  grid_dependency_wait(); // the counts come from the launch before this one (count stage / previous scatter of a batch)
   uint32_t n = load_n(id);
 
   int s = 0;
@@ -719,7 +712,6 @@ __global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LE
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  grid_launch_dependents(); // the next view's scatter of a batch may start filling its ring as CTAs of this one retire
 
   if (warp == 0)
   {
@@ -764,8 +756,6 @@ __global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LE
   if (warp == NW + 1)
   {
     // ===== the next view's count stage (smesh_fuse_add_batch): hidden under this view's scatter =====
-    // (the array it writes is the one the PREVIOUS view's scatter reads: that launch must be over, not just started)
-    grid_dependency_wait();
     count_job_warp(a.next_ids, a.next_npix, (uint32_t) a.P, a.next_counts, a.next_tag, lane);
     return;
   }
@@ -805,7 +795,6 @@ __global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LE
   int64_t tile = blockIdx.x;
   uint2 id = load_ids(tile), id1 = load_ids(tile + tile_stride);
   float2 wt = load_wts(tile), wt1 = load_wts(tile + tile_stride);
-  grid_dependency_wait(); // the counts come from the launch before this one (count stage / previous scatter of a batch)
   uint2 n = make_uint2(load_n(id.x), load_n(id.y));
 
   int s = 0;
@@ -1495,25 +1484,6 @@ static size_t ring_smem_bytes(int C, const RingConfig& cfg)
   return (size_t) cfg.stages * cfg.consumer_warps * 32 * C * 4 + (size_t) cfg.stages * 16;
 }
 
-// <<<>>> with the programmatic-stream-serialization attribute when args.pdl is set (see grid_dependency_wait())
-template <typename Kernel>
-static cudaError_t launch_ring_kernel(Kernel kernel, unsigned blocks, int threads, size_t smem, cudaStream_t stream,
-                                      const ScatterArgs& args)
-{
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(blocks);
-  cfg.blockDim = dim3((unsigned) threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  static const bool no_pdl = getenv("SMESH_NO_PDL") != nullptr; // profiling only
-  cfg.attrs = attr;
-  cfg.numAttrs = (args.pdl && !no_pdl) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, args);
-}
-
 template <int KIND, int CT>
 static int launch_scatter_ring(const ScatterArgs& args_in, const RingConfig& cfg, cudaStream_t stream)
 {
@@ -1538,7 +1508,7 @@ static int launch_scatter_ring(const ScatterArgs& args_in, const RingConfig& cfg
   int64_t blocks = (int64_t) num_sms() * blocks_per_sm;
   if (blocks > args.ntiles) blocks = args.ntiles;
   if (blocks < 1) return SMESH_OK;
-  SMESH_CUDA_CHECK(launch_ring_kernel(kernel, (unsigned) blocks, threads, smem, stream, args));
+  kernel<<<(unsigned) blocks, threads, smem, stream>>>(args);
   SMESH_LAUNCH_CHECK("scatter_kernel");
   return SMESH_OK;
 }
@@ -1599,7 +1569,7 @@ static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
   int64_t blocks = (int64_t) num_sms() * (env_ctas >= 1 && env_ctas < blocks_per_sm ? env_ctas : blocks_per_sm);
   if (blocks > args.ntiles) blocks = args.ntiles;
   if (blocks < 1) return SMESH_OK;
-  SMESH_CUDA_CHECK(launch_ring_kernel(kernel, (unsigned) blocks, threads, smem, stream, args));
+  kernel<<<(unsigned) blocks, threads, smem, stream>>>(args);
   SMESH_LAUNCH_CHECK("scatter_pair_kernel");
   return SMESH_OK;
 }
@@ -1656,7 +1626,7 @@ static int launch_scatter(const ScatterArgs& args, cudaStream_t stream)
   return SMESH_OK;
 }
 
-// SMESH_COUNT_VARIANT (tuning / profiling): 0 = flat runs (default); 4 = flat runs, 8 groups per warp iteration; 1 / 2 / 3 = blocks of 8 / 4 / 2 columns with runs folded
+// SMESH_COUNT_VARIANT (tuning / profiling): 0 = flat runs (default); 1 / 2 / 3 = blocks of 8 / 4 / 2 columns with runs folded
 // across columns; 10 / 11 = variants 0 / 1 without their reductions (the floor of the id traffic and the bookkeeping).
 // Measured on cfg3 (profiles/r02b_count_variants.txt): folding halves the reductions (1.38 M -> 0.64 M L2 sectors) but
 // doubles the instructions and is slower (11.3 vs 8.3 us): the stage is bound by launch + load latency (5.4 us without
@@ -1675,16 +1645,13 @@ static int launch_count(const void* ids, int64_t so, int64_t si, int64_t n_outer
   const IdT* p = static_cast<const IdT*>(ids);
   const int64_t npix = n_outer * n_inner;
   const int64_t cap = (int64_t) num_sms() * 8;
-  if (variant == 0 || variant == 10 || variant == 4)
+  if (variant == 0 || variant == 10)
   {
     const bool flat = (si == 1 || n_inner == 1) && (so == n_inner || n_outer == 1);
-    const int unroll = variant == 4 ? 8 : COUNT_UNROLL;
-    const int64_t per_block = (256 / 32) * 32 * unroll;
+    const int64_t per_block = (256 / 32) * 32 * COUNT_UNROLL;
     int64_t blocks = std::min((npix + per_block - 1) / per_block, cap);
     if (variant == 0)
       count_runs_kernel<IdT, true, COUNT_UNROLL><<<(unsigned) blocks, 256, 0, stream>>>(p, so, si, n_inner, npix, P, counts, ids32, flat ? 1 : 0, epoch);
-    else if (variant == 4)
-      count_runs_kernel<IdT, true, 8><<<(unsigned) blocks, 256, 0, stream>>>(p, so, si, n_inner, npix, P, counts, ids32, flat ? 1 : 0, epoch);
     else
       count_runs_kernel<IdT, false, COUNT_UNROLL><<<(unsigned) blocks, 256, 0, stream>>>(p, so, si, n_inner, npix, P, counts, ids32, flat ? 1 : 0, epoch);
     SMESH_LAUNCH_CHECK("count_runs_kernel");
@@ -1757,16 +1724,17 @@ static ScatterArgs make_scatter_args(const uint32_t* ids32, const float* probs, 
   args.next_counts = nullptr;
   args.next_npix = 0;
   args.next_tag = 0;
-  args.pdl = 0;
   return args;
 }
 
 static bool scatter_takes_count_job(int kind, const ScatterArgs& args)
 {
-  // mirrors launch_scatter(): class-parallel kernel for wide C (no spare warp), else a ring kernel if the image is aligned
+  // mirrors launch_scatter(): class-parallel kernel for wide C (no spare warp), else a ring kernel if the image is aligned.
+  // summax: its scatter is one scalar reduction per run - with the count warp beside it the launch was measured slower
+  // than the two stages one after the other (cfg3: 46.8 vs 38.9 us per view), so it takes none.
   int vw = 1;
   RingConfig cfg;
-  if (kind != SMESH_KIND_SUMMAX && rows_kernel_takes(args, vw))
+  if (kind == SMESH_KIND_SUMMAX || rows_kernel_takes(args, vw))
   {
     return false;
   }
@@ -1808,12 +1776,10 @@ struct ViewStages
   }
 
   // next / next_counts / next_epoch: the view whose count stage rides along (NULL = none); see ScatterArgs
-  // pdl: the launch before this one on the stream is this view's count stage, or the scatter that carried it
-  int scatter(uint32_t* counts, uint32_t epoch, cudaStream_t stream, bool pdl, const ViewStages* next = nullptr,
+  int scatter(uint32_t* counts, uint32_t epoch, cudaStream_t stream, const ViewStages* next = nullptr,
               uint32_t* next_counts = nullptr, uint32_t next_epoch = 0) const
   {
     ScatterArgs args = make_scatter_args(flat_ids(), probs, weights, counts, acc, npix(), C, P, iew, epoch);
-    args.pdl = (pdl && epoch != 0) ? 1 : 0;
     if (next != nullptr)
     {
       args.next_ids = next->flat_ids();
@@ -1878,7 +1844,7 @@ static int add_view(int kind, const void* ids, int id_dtype, int64_t ids_so, int
     return rc;
   }
   rc = v.count(counts, epoch, stream);
-  return rc != SMESH_OK ? rc : v.scatter(counts, epoch, stream, true);
+  return rc != SMESH_OK ? rc : v.scatter(counts, epoch, stream);
 }
 
 static int check_add_args(const char* fn, int kind, const void* ids, const float* probs, int64_t n_outer, int64_t n_inner,
@@ -2062,9 +2028,8 @@ extern "C" int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id
               scatter_takes_count_job(kind, make_scatter_args(v.flat_ids(), v.probs, v.weights, counts_of(b), acc, v.npix(), C, P,
                                                               iew, epoch_of(b)));
     }
-    // (the launch before this scatter is view b's count stage or the scatter of view b-1 that carried it)
-    rc = carry ? v.scatter(counts_of(b), epoch_of(b), stream, true, &vn, counts_of(b + 1), epoch_of(b + 1))
-               : v.scatter(counts_of(b), epoch_of(b), stream, true);
+    rc = carry ? v.scatter(counts_of(b), epoch_of(b), stream, &vn, counts_of(b + 1), epoch_of(b + 1))
+               : v.scatter(counts_of(b), epoch_of(b), stream);
     if (rc != SMESH_OK)
     {
       return rc;
