@@ -9,8 +9,8 @@
  * Conventions
  *   - plain C types only; every pointer is a DEVICE pointer unless its name ends in _host;
  *   - the caller owns every buffer (the Python layer holds them as torch tensors); the library keeps no state between
- *     calls except the per-thread error string, per-kernel launch configuration and the side stream of
- *     smesh_fuse_add_batch, so it is safe to use from several host threads / streams;
+ *     calls except the per-thread error string and the per-kernel launch configuration, so it is safe to use from
+ *     several host threads / streams;
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and never synchronises the device;
  *   - return value 0 = success; anything else is an smesh_status and smesh_last_error() describes it
  *     (SMESH_ERR_INVALID_ARGUMENT maps to the reference's std::invalid_argument -> Python ValueError);
@@ -194,14 +194,29 @@ int smesh_fuse_scatter(int kind, const uint32_t* ids32, const float* probs, cons
 int smesh_fuse_clear(const uint32_t* ids32, int64_t n_pix, int64_t P, uint32_t* counts, void* stream);
 
 /*
+ * One view's scatter stage with the NEXT view's count stage riding in the same launch (one extra warp per CTA of the ring
+ * kernels counts the next index image while the others scatter this view; where the kernel has no spare warp the next
+ * count is a launch of its own): what smesh_fuse_add_batch does between its views, for callers that hold the next index
+ * image early - a pipeline that renders one view ahead. Flat uint32 ids, tagged epochs only:
+ *   counts / count_epoch            this view's counter array and epoch; counted != 0: the counts are already in place
+ *                                   (a previous call carried them, or smesh_raster_render_counted), else they are taken first
+ *   next_ids32 / next_n_pix         the next view's flat index image (may have another size)
+ *   next_counts / next_epoch        the OTHER counter array and an epoch of the other parity
+ * On completion next_counts holds the next view's counts: follow with this function again (counted = 1) or with
+ * smesh_fuse_scatter(ids32 = next_ids32, counts = next_counts, count_epoch = next_epoch).
+ */
+int smesh_fuse_scatter_count_next(int kind, const uint32_t* ids32, const float* probs, const float* weights, int64_t n_pix,
+                                  int C, int64_t P, float iew, uint32_t* counts, uint32_t count_epoch, int counted,
+                                  const uint32_t* next_ids32, int64_t next_n_pix, uint32_t* next_counts, uint32_t next_epoch,
+                                  float* acc, void* stream);
+
+/*
  * A batch of B views with identical shapes, view b at ids + b*ids_stride_view (elements), probs + b*probs_stride_view
  * (floats), weights + b*w_stride_view (floats, if weights != NULL). Equivalent to B calls of smesh_fuse_add in order with
  * epochs count_epoch0, count_epoch0 + 1, ... (all <= 255), or all 0.
  *   counts2  uint32[2][P]: TWO counter arrays; the view with epoch e counts into array e & 1 (epoch 0: array 0 only).
- *            With tagged epochs and 32-bit flat ids the count stage of view b+1 runs on an internal side stream (one
- *            per host thread and device, created on first use) under the scatter stage of view b; the side stream has
- *            joined `stream` again when the call returns, so the call is still stream-ordered for the caller and may
- *            be captured into a CUDA graph.
+ *            With tagged epochs and 32-bit flat ids the count stage of view b+1 rides in the scatter launch of view b
+ *            (one extra warp per CTA of the ring kernels), so a batch costs one count launch plus B scatter launches.
  */
 int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id_dtype, int64_t ids_stride_view,
                          int64_t ids_stride_outer, int64_t ids_stride_inner, const float* probs,

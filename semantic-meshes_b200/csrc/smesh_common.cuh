@@ -67,20 +67,38 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+// hint: suspend-time hint of mbarrier.try_wait in ns (the thread may sleep in hardware until the phase completes instead of
+// coming back to poll); 0 = plain polling
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t hint = 0x989680u)
 {
-  asm volatile(
-    "{\n"
-    ".reg .pred p;\n"
-    "SMESH_WAIT_%=:\n"
-    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-    "@p bra SMESH_DONE_%=;\n"
-    "bra SMESH_WAIT_%=;\n"
-    "SMESH_DONE_%=:\n"
-    "}\n" ::"r"(smem_u32(bar)),
-    "r"(parity), "r"(0x989680u) // suspend-time hint: the thread sleeps in hardware until the phase completes instead of
-                                // coming back to poll (the polling of 592 producers was 5 M warp instructions per view)
-    : "memory");
+  if (hint != 0u)
+  {
+    asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SMESH_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra SMESH_DONE_%=;\n"
+      "bra SMESH_WAIT_%=;\n"
+      "SMESH_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(hint)
+      : "memory");
+  }
+  else
+  {
+    asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SMESH_WAITP_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SMESH_DONEP_%=;\n"
+      "bra SMESH_WAITP_%=;\n"
+      "SMESH_DONEP_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+  }
 }
 
 __device__ __forceinline__ uint64_t l2_evict_first_policy()

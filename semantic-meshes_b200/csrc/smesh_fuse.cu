@@ -345,6 +345,7 @@ struct ScatterArgs
   uint32_t count_mask;     // COUNT_MASK with a tagged epoch, 0xFFFFFFFF without
   uint32_t run_cap;        // power of two <= 32: runs of equal ids are cut every run_cap lanes
   int mul_exact;           // mul: the reference's powf + logf sequence for every element (see neg_log_pow)
+  uint32_t wait_hint;      // suspend-time hint of the ring's mbarrier waits (see mbar_wait)
   // Optional second job of the ring kernels: the count stage of the NEXT view of a batch (smesh_fuse_add_batch), done by
   // one extra warp per CTA while the consumer warps scatter this view. NULL = none.
   const uint32_t* next_ids;   // [next_npix] flat uint32 ids of the next view
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(320) scatter_kernel(ScatterArgs a)
       {
         if (!first_pass)
         {
-          mbar_wait(empty_bar + s, use_parity);
+          mbar_wait(empty_bar + s, use_parity, a.wait_hint);
         }
         const int64_t px0 = tile * tile_px;
         const int64_t px_n = min((int64_t) tile_px, a.npix - px0);
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(320) scatter_kernel(ScatterArgs a)
     const uint32_t n1 = load_n(id1);
 
     const bool valid = id < P32;
-    mbar_wait(full_bar + s, parity);
+    mbar_wait(full_bar + s, parity, a.wait_hint);
     const float* row = stage_ptr + stage_floats * s;
 
     // ---- gate (Mesh.h:95-98): sequential float sum of the class vector > 0.5 ----
@@ -725,7 +726,7 @@ __global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LE
       {
         if (!first_pass)
         {
-          mbar_wait(empty_bar + s, use_parity);
+          mbar_wait(empty_bar + s, use_parity, a.wait_hint);
         }
         const int64_t px0 = tile * tile_px;
         const int64_t px_n = min((int64_t) tile_px, a.npix - px0);
@@ -806,7 +807,7 @@ __global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LE
     const float2 wt2 = load_wts(tile + 2 * tile_stride);
     const uint2 n1 = make_uint2(load_n(id1.x), load_n(id1.y));
 
-    mbar_wait(full_bar + s, parity);
+    mbar_wait(full_bar + s, parity, a.wait_hint);
     const float2* row2 = reinterpret_cast<const float2*>(stage_ptr + stage_floats * s);
     // ---- both pixels' class vectors: 2C contiguous floats, C 64-bit loads ----
     float ab[2 * C];
@@ -1720,6 +1721,8 @@ static ScatterArgs make_scatter_args(const uint32_t* ids32, const float* probs, 
   const char* mul_exact_env = getenv("SMESH_MUL_EXACT"); // read per call: tests switch it
   args.mul_exact = (mul_exact_env != nullptr && atoi(mul_exact_env) != 0) ? 1 : 0;
   args.iew = iew;
+  static const uint32_t wait_hint = getenv("SMESH_WAIT_HINT") ? (uint32_t) strtoul(getenv("SMESH_WAIT_HINT"), nullptr, 0) : 0x989680u;
+  args.wait_hint = wait_hint;
   args.next_ids = nullptr;
   args.next_counts = nullptr;
   args.next_npix = 0;
@@ -1942,6 +1945,71 @@ extern "C" int smesh_fuse_scatter(int kind, const uint32_t* ids32, const float* 
   }
   return launch_scatter_kind(kind, make_scatter_args(ids32, probs, weights, counts, acc, n_pix, C, P, iew, count_epoch),
                              static_cast<cudaStream_t>(stream_v));
+}
+
+extern "C" int smesh_fuse_scatter_count_next(int kind, const uint32_t* ids32, const float* probs, const float* weights,
+                                            int64_t n_pix, int C, int64_t P, float iew, uint32_t* counts, uint32_t count_epoch,
+                                            int counted, const uint32_t* next_ids32, int64_t next_n_pix, uint32_t* next_counts,
+                                            uint32_t next_epoch, float* acc, void* stream_v)
+{
+  if (n_pix < 0 || next_n_pix < 0 || C < 1 || P < 0 || kind < 0 || kind > 2 ||
+      (n_pix > 0 && P > 0 && (!ids32 || !probs || !counts || !acc)) || (next_n_pix > 0 && P > 0 && (!next_ids32 || !next_counts)))
+  {
+    set_error("smesh_fuse_scatter_count_next: invalid argument");
+    return SMESH_ERR_INVALID_ARGUMENT;
+  }
+  if (C > 4096 || P >= 0xFFFFFFFFll)
+  {
+    set_error("smesh_fuse_scatter_count_next: unsupported size (C=%d must be <= 4096, P=%lld < 2^32-1)", C, (long long) P);
+    return SMESH_ERR_UNSUPPORTED;
+  }
+  if (count_epoch == 0 || next_epoch == 0 || count_epoch > 255u || next_epoch > 255u || ((count_epoch ^ next_epoch) & 1u) == 0u ||
+      next_counts == counts || n_pix > (int64_t) COUNT_MASK || next_n_pix > (int64_t) COUNT_MASK)
+  {
+    set_error("smesh_fuse_scatter_count_next: needs tagged epochs 1..255 of different parity in two counter arrays");
+    return SMESH_ERR_INVALID_ARGUMENT;
+  }
+  if (P == 0)
+  {
+    return SMESH_OK;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  int rc = SMESH_OK;
+  if (!counted && n_pix > 0)
+  {
+    rc = launch_count_any("smesh_fuse_scatter_count_next", SMESH_ID_U32, ids32, n_pix, 1, 1, n_pix, P, counts, nullptr, count_epoch,
+                          stream);
+    if (rc != SMESH_OK)
+    {
+      return rc;
+    }
+  }
+  bool carried = false;
+  if (n_pix > 0)
+  {
+    ScatterArgs args = make_scatter_args(ids32, probs, weights, counts, acc, n_pix, C, P, iew, count_epoch);
+    static const bool no_overlap = getenv("SMESH_NO_BATCH_OVERLAP") != nullptr; // profiling only
+    if (next_n_pix > 0 && !no_overlap && scatter_takes_count_job(kind, args))
+    {
+      args.next_ids = next_ids32;
+      args.next_counts = next_counts;
+      args.next_npix = next_n_pix;
+      args.next_tag = next_epoch << COUNT_BITS;
+      carried = true;
+    }
+    rc = launch_scatter_kind(kind, args, stream);
+    if (rc != SMESH_OK)
+    {
+      return rc;
+    }
+  }
+  if (!carried && next_n_pix > 0)
+  {
+    // this view's scatter kernel has no spare warp: the next view's count stage is a launch of its own
+    rc = launch_count_any("smesh_fuse_scatter_count_next", SMESH_ID_U32, next_ids32, next_n_pix, 1, 1, next_n_pix, P, next_counts,
+                          nullptr, next_epoch, stream);
+  }
+  return rc;
 }
 
 extern "C" int smesh_fuse_clear(const uint32_t* ids32, int64_t n_pix, int64_t P, uint32_t* counts, void* stream_v)

@@ -32,6 +32,8 @@ SIGNATURES = {
                               _vp, _vp, _vp]),
     "smesh_fuse_count": (_int, [_vp, _int, _i64, _i64, _i64, _i64, _i64, _vp, _u32, _vp, _vp]),
     "smesh_fuse_scatter": (_int, [_int, _vp, _vp, _vp, _i64, _int, _i64, _f32, _vp, _u32, _vp, _vp]),
+    "smesh_fuse_scatter_count_next": (_int, [_int, _vp, _vp, _vp, _i64, _int, _i64, _f32, _vp, _u32, _int, _vp, _i64, _vp, _u32,
+                                             _vp, _vp]),
     "smesh_fuse_clear": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "smesh_fuse_add_batch": (_int, [_int, _i64, _vp, _int, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64,
                                     _int, _i64, _f32, _vp, _u32, _vp, _vp, _vp]),
