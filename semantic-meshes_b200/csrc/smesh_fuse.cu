@@ -312,6 +312,14 @@ __device__ __forceinline__ void count_job_warp(const uint32_t* __restrict__ ids,
   }
 }
 
+// (out of line for scatter_kernel: inlined, the job changed the register allocation of the consumers' loop and the C = 40
+// kernel lost a quarter of its speed)
+__device__ __noinline__ void count_job_warp_call(const uint32_t* ids, int64_t npix, uint32_t P32, uint32_t* counts, uint32_t tag,
+                                                 int lane)
+{
+  count_job_warp(ids, npix, P32, counts, tag, lane);
+}
+
 __global__ void __launch_bounds__(256) clear_kernel(const uint32_t* __restrict__ ids32, int64_t npix, int64_t P,
                                                     uint32_t* __restrict__ counts)
 {
@@ -392,15 +400,15 @@ __device__ __forceinline__ void load_chunk(const float* __restrict__ p, int nval
 }
 
 // Shared memory: [stages][NW*32*C] floats | full[stages], empty[stages] mbarriers
-template <int KIND, int CT>
-__global__ void __launch_bounds__(320) scatter_kernel(ScatterArgs a)
+// RIDER: the CTA has one more warp, which runs the next view's count stage (see ScatterArgs)
+template <int KIND, int CT, bool RIDER>
+__global__ void __launch_bounds__(RIDER ? 320 : 288, RIDER ? 3 : 0) scatter_kernel(ScatterArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int C = CT > 0 ? CT : a.C;
   const int Cpad = CT > 0 ? ((CT + 3) & ~3) : a.Cpad;
   const int al = (C % 4 == 0) ? 4 : ((C % 2 == 0) ? 2 : 1);
-  const bool has_count = a.next_ids != nullptr;
-  const int NW = (int) (blockDim.x >> 5) - 1 - (has_count ? 1 : 0); // consumer warps; warp 0 produces, the last one may count
+  const int NW = (int) (blockDim.x >> 5) - 1 - (RIDER ? 1 : 0); // consumer warps; warp 0 produces, the last one may count
   const int tile_px = NW * 32;
   const size_t stage_floats = (size_t) tile_px * C;
   const int stages = a.stages;
@@ -464,10 +472,10 @@ __global__ void __launch_bounds__(320) scatter_kernel(ScatterArgs a)
     return;
   }
 
-  if (warp == NW + 1)
+  if (RIDER && warp == NW + 1)
   {
     // ===== the next view's count stage (smesh_fuse_add_batch) =====
-    count_job_warp(a.next_ids, a.next_npix, (uint32_t) a.P, a.next_counts, a.next_tag, lane);
+    count_job_warp_call(a.next_ids, a.next_npix, (uint32_t) a.P, a.next_counts, a.next_tag, lane);
     return;
   }
 
@@ -1490,8 +1498,9 @@ static int launch_scatter_ring(const ScatterArgs& args_in, const RingConfig& cfg
 {
   ScatterArgs args = args_in;
   const size_t smem = ring_smem_bytes(args.C, cfg);
-  auto kernel = scatter_kernel<KIND, CT>;
-  const int threads = (cfg.consumer_warps + 1 + (args.next_ids != nullptr ? 1 : 0)) * 32;
+  const bool rider = args.next_ids != nullptr;
+  auto kernel = rider ? scatter_kernel<KIND, CT, true> : scatter_kernel<KIND, CT, false>;
+  const int threads = (cfg.consumer_warps + 1 + (rider ? 1 : 0)) * 32;
   int blocks_per_sm = 0;
   const int cfg_rc = kernel_blocks_per_sm(reinterpret_cast<const void*>(kernel), threads, smem, &blocks_per_sm);
   if (cfg_rc != SMESH_OK)

@@ -254,10 +254,14 @@ class MeshAggregator:
         return self._ids32
 
     # ---------------------------------------------------------------------------------------------------------------
-    def add(self, primitive_indices, probs, weights=None):
+    def add(self, primitive_indices, probs, weights=None, count_next=None):
         """Fuse one view (ModelAggregator::add, Mesh.h:65-107). If `primitive_indices` comes from
-        `renderer.render(camera, count_into=self)` the per-face pixel counts are already in place and only the scatter
-        stage runs.
+        `renderer.render(camera, count_into=self)`, or was the `count_next` of the previous add, the per-face pixel counts
+        are already in place and only the scatter stage runs.
+
+        count_next (extension): the index image of the view that will be added NEXT (a device int32 tensor, e.g. from a
+        renderer running one view ahead). Its count stage then rides in this view's scatter launch (one extra warp per
+        CTA, smesh_fuse_scatter_count_next) instead of being a launch of its own in front of the next scatter.
 
         The kernels are asynchronous on the current CUDA stream (the reference's add is synchronous); host inputs have
         been read when the call returns, so the caller may reuse its buffers like with the reference (set
@@ -268,30 +272,64 @@ class MeshAggregator:
         if lay is None or self.primitives == 0:
             return
         pr, wt, n_outer, n_inner, ids_so, ids_si, w_so, w_si = lay
+        npix = n_outer * n_inner
         stream = torch.cuda.current_stream().cuda_stream
+        flat32 = ((ids.dtype == torch.int32 and self.primitives <= 0x7FFFFFFF) or ids.dtype == torch.uint32) \
+            and (ids_si == 1 or n_inner == 1) and (ids_so == n_inner or n_outer == 1)
         token = getattr(primitive_indices, "_smesh_counted", None)
-        if (token is not None and token[0] == id(self) and token[1] == self._epoch_gen and ids.dtype == torch.int32
-                and self._array_epoch[token[2] & 1] == token[2]  # no later view has counted into that array since
-                and (ids_si == 1 or n_inner == 1) and (ids_so == n_inner or n_outer == 1)):
+        counted = (token is not None and token[0] == id(self) and token[1] == self._epoch_gen and flat32
+                   and self._array_epoch[token[2] & 1] == token[2])  # no later view has counted into that array since
+        nxt = self._rider_candidate(count_next) if count_next is not None else None
+        # this view's scatter can carry the next view's count stage: two epochs without a wrap, and the next view's counter
+        # array (epoch parity) is not the one this view's counts sit in
+        if (nxt is not None and flat32 and npix < (1 << 24) and self._epoch + 2 <= 255
+                and (not counted or ((self._epoch + 1) ^ token[2]) & 1)):
+            epoch = token[2] if counted else self._next_epochs(npix)
+            self._enter()
+            epoch2 = self._next_epochs(nxt.numel())
+            with torch.cuda.device(self.device):
+                rc = _lib.lib.smesh_fuse_scatter_count_next(
+                    self._kind, ids.data_ptr(), pr.data_ptr(), wt.data_ptr() if wt is not None else None, npix,
+                    self.classes, self.primitives, self.images_equal_weight, self._counts_for(epoch).data_ptr(), epoch,
+                    1 if counted else 0, nxt.data_ptr(), nxt.numel(), self._counts_for(epoch2).data_ptr(), epoch2,
+                    self._acc.data_ptr(), stream)
+            self._release_stage()
+            _lib.check(rc)
+            count_next._smesh_counted = (id(self), self._epoch_gen, epoch2)
+            return
+        if counted:
             epoch = token[2]
             self._enter()
             with torch.cuda.device(self.device):
                 rc = _lib.lib.smesh_fuse_scatter(self._kind, ids.data_ptr(), pr.data_ptr(),
-                                                 wt.data_ptr() if wt is not None else None, n_outer * n_inner, self.classes,
+                                                 wt.data_ptr() if wt is not None else None, npix, self.classes,
                                                  self.primitives, self.images_equal_weight,
                                                  self._counts_for(epoch).data_ptr(), epoch, self._acc.data_ptr(), stream)
             self._release_stage()
             _lib.check(rc)
             return
-        epoch = self._next_epochs(n_outer * n_inner)
+        epoch = self._next_epochs(npix)
         with torch.cuda.device(self.device):
             rc = _lib.lib.smesh_fuse_add(self._kind, ids.data_ptr(), id_dtype, ids_so, ids_si, pr.data_ptr(),
                                          wt.data_ptr() if wt is not None else None, w_so, w_si, n_outer, n_inner,
                                          self.classes, self.primitives, self.images_equal_weight,
                                          self._counts_for(epoch).data_ptr(), epoch,
-                                         self._scratch(n_outer * n_inner).data_ptr(), self._acc.data_ptr(), stream)
+                                         self._scratch(npix).data_ptr(), self._acc.data_ptr(), stream)
         self._release_stage()
         _lib.check(rc)
+
+    def _rider_candidate(self, count_next):
+        """The next view's index image if its count stage can ride in this view's scatter launch: a contiguous int32 /
+        uint32 device tensor of fewer than 2^24 pixels (the histogram does not depend on the pixel order)."""
+        torch = self._torch
+        t = count_next
+        if not isinstance(t, torch.Tensor) or t.device != self.device or t.dim() != 2 or not t.is_contiguous():
+            return None
+        if not (t.dtype == torch.uint32 or (t.dtype == torch.int32 and self.primitives <= 0x7FFFFFFF)):
+            return None
+        if t.numel() == 0 or t.numel() >= (1 << 24) or t.data_ptr() % 4 != 0:
+            return None
+        return t
 
     def add_batch(self, primitive_indices, probs, weights=None):
         """Extension: fuse B views held in batched device tensors (B,W,H) / (B,W,H,C) / (B,W,H) with one call; the same

@@ -12,9 +12,11 @@ from . import _lib
 
 
 class ViewPipeline:
-    def __init__(self, renderer, aggregator, fused_count=False):
+    def __init__(self, renderer, aggregator, fused_count=False, count_ahead=True):
         torch = _lib.require_cuda()
         self.fused_count = bool(fused_count)
+        # count_ahead: the count stage of view v+1 rides in the scatter launch of view v (MeshAggregator.add(count_next=))
+        self.count_ahead = bool(count_ahead)
         self._torch = torch
         self.renderer, self.aggregator = renderer, aggregator
         with torch.cuda.device(renderer.device):
@@ -45,7 +47,14 @@ class ViewPipeline:
             if pending is not None:
                 idx_prev, ev_prev = pending
                 main.wait_event(ev_prev)
-                self.aggregator.add(idx_prev, predictions[v - 1], None if weights is None else weights[v - 1])
+                ride = None
+                if self.count_ahead and not fused and nxt is not None:
+                    # the fusion of view v-1 waits for the render of view v as well and counts it on the way (the renderer
+                    # is then two views ahead of the fusion instead of one: same throughput, one launch less per view)
+                    main.wait_event(nxt[1])
+                    ride = nxt[0]
+                    ride.record_stream(main)
+                self.aggregator.add(idx_prev, predictions[v - 1], None if weights is None else weights[v - 1], count_next=ride)
                 idx_prev.record_stream(main)
                 ev_add = torch.cuda.Event()
                 ev_add.record(main)

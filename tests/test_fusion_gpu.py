@@ -761,3 +761,44 @@ def test_full_size_against_genuine_reference_aggregator(sm, name, kinds):
         ref.close()
         assert (exp.sum(-1) > 0.5).sum() > 100000
         assert_get_close(kind, got, exp)
+
+
+@pytest.mark.parametrize("kind,C", [("sum", 19), ("mul", 19), ("summax", 19), ("sum", 40), ("sum", 150), ("sum", 3)])
+def test_add_with_count_next_chain(sm, kind, C):
+    """add(ids_v, probs_v, count_next=ids_{v+1}): the next view's count stage rides in this view's scatter launch (or is a
+    launch of its own where the scatter kernel has no spare warp: summax, wide C), and the next add finds its counts in
+    place. A chain of views of changing size, a break in the chain (a plain add in between voids nothing it should not),
+    an unused count_next, and more than 255 views (the epoch wraps: the chain restarts) - always the plain loop's result."""
+    import torch
+    rng = np.random.default_rng(C * 7 + len(kind))
+    P = 300
+    shapes = [(96, 130), (96, 130), (64, 72), (96, 130), (31, 33), (96, 130)]
+    views = [make_view(rng, W, H, C, P, block=1 + (v % 4)) for v, (W, H) in enumerate(shapes)]
+    dev = [(torch.from_numpy(i.view(np.int32)).cuda(), torch.from_numpy(p).cuda()) for i, p in views]
+    ref = oracle.Aggregator(P, C, kind)
+    agg = sm.fusion.MeshAggregator(P, C, kind)
+    n = len(dev)
+    for v in range(n):
+        agg.add(dev[v][0], dev[v][1], count_next=dev[v + 1][0] if v + 1 < n else None)
+        ref.add(*views[v])
+    assert_acc_close(kind, agg.state().cpu().numpy(), ref.acc)
+    # a break in the chain: view 1 is counted ahead, then two other views are added, then view 1
+    agg.add(dev[0][0], dev[0][1], count_next=dev[1][0])
+    agg.add(dev[2][0], dev[2][1])
+    agg.add(dev[3][0], dev[3][1], count_next=dev[4][0])      # dev[4] is counted but never added right away
+    agg.add(dev[1][0], dev[1][1])                            # its token is stale by now: recount
+    agg.add(dev[4][0], dev[4][1])
+    for v in (0, 2, 3, 1, 4):
+        ref.add(*views[v])
+    assert_acc_close(kind, agg.state().cpu().numpy(), ref.acc, rtol=2e-5)
+    # a long chain across the epoch wrap
+    agg.reset()
+    ref.reset()
+    for v in range(300):
+        agg.add(dev[v % n][0], dev[v % n][1], count_next=dev[(v + 1) % n][0])
+    for v in range(n):
+        ref.add(*views[v])
+    exp = ref.acc * 50
+    if kind == "mul":
+        exp = np.where(np.isinf(ref.acc), ref.acc, exp)
+    assert_acc_close(kind, agg.state().cpu().numpy(), exp, rtol=5e-5)
