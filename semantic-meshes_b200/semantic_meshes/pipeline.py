@@ -12,10 +12,12 @@ from . import _lib
 
 
 class ViewPipeline:
-    def __init__(self, renderer, aggregator, fused_count=False, count_ahead=True):
+    def __init__(self, renderer, aggregator, fused_count=False, count_ahead=False):
         torch = _lib.require_cuda()
         self.fused_count = bool(fused_count)
-        # count_ahead: the count stage of view v+1 rides in the scatter launch of view v (MeshAggregator.add(count_next=))
+        # count_ahead: the count stage of view v+1 rides in the scatter launch of view v (MeshAggregator.add(count_next=)).
+        # Off by default: the fusion of view v then has to wait for the render of view v+1, the two streams fall into
+        # lock step and the tail of every render runs alone - measured 11.1 k against 12.4 k views/s at config 3.
         self.count_ahead = bool(count_ahead)
         self._torch = torch
         self.renderer, self.aggregator = renderer, aggregator

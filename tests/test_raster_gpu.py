@@ -580,3 +580,25 @@ def test_full_size_cfg4_bit_exact(sm):
     gi, gd, oi, od = render_both(sm, mesh, cams[0])
     assert_bit_exact(gi, gd, oi, od)
     assert (gi != BG).mean() > 0.9
+
+
+def test_pipeline_count_ahead_matches_sequential(sm):
+    """ViewPipeline(count_ahead=True): the count stage of view v+1 rides in the scatter launch of view v."""
+    import torch
+    from semantic_meshes import synthetic
+    from semantic_meshes.pipeline import ViewPipeline
+    W, H, C = 160, 120, 19
+    mesh = synthetic.mesh("terrain", 6000, seed=2)
+    renderer = sm.render.triangles(mesh)
+    P = renderer.getPrimitivesNum()
+    cams = synthetic.terrain_cameras(7, W, H, 6000, tris_per_view=1500, seed=8)
+    preds = torch.stack([synthetic.predictions_torch(W, H, C, seed=v, device="cuda") for v in range(len(cams))])
+    seq, ovl = sm.fusion.MeshAggregator(P, C), sm.fusion.MeshAggregator(P, C)
+    for v, cam in enumerate(cams):
+        idx, _ = renderer.render(cam)
+        seq.add(idx, preds[v])
+    pipe = ViewPipeline(renderer, ovl, count_ahead=True)
+    pipe.run(cams, preds)
+    pipe.run(cams, preds)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(ovl.state(), 2 * seq.state(), rtol=1e-5, atol=1e-6)
