@@ -402,25 +402,11 @@ def run_ours(args, cfg):
         else:
             # same work, render of view v+1 overlapped with the fusion of view v (two streams)
             pipe.run([c for c, _ in view_list], [scene.probs[b] for _, b in view_list])
-        if strong:
-            agg.allreduce()
 
-    # ---- device-resident throughput: the step as a CUDA graph ----
+    # ---- device-resident throughput: the step's views as a CUDA graph ----
     use_graph = not args.no_graph
-    step()  # warm the library's per-kernel configuration, the communicator and the allocator before capture
+    step()  # warm the library's per-kernel configuration and the allocator before capture
     torch.cuda.synchronize()
-    graph = None
-    if use_graph and not (strong and world > 1):  # NCCL inside a capture is not worth the risk: strong jobs run eagerly
-        try:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                step()
-        except Exception as e:  # pragma: no cover
-            sys.stderr.write(f"CUDA graph capture failed ({e!r}); timing eager launches\n")
-            graph = None
-            torch.cuda.synchronize()
-    run_step = graph.replay if graph is not None else step
-
     # the communicator's first collective of this size pays for its setup: do one before the timed region, and time it
     allreduce_cold_ms = allreduce_warm_ms = None
     if dist is not None:
@@ -438,6 +424,23 @@ def run_ours(args, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         allreduce_cold_ms, allreduce_warm_ms = float(t[0]), float(t[1])
         del scratch
+
+    graph = None
+    if use_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+        except Exception as e:  # pragma: no cover
+            sys.stderr.write(f"CUDA graph capture failed ({e!r}); timing eager launches\n")
+            graph = None
+            torch.cuda.synchronize()
+    run_views = graph.replay if graph is not None else step
+
+    def run_step():
+        run_views()
+        if strong:
+            agg.allreduce()  # a job ends with its all-reduce (NCCL launched eagerly behind the graph replay)
 
     agg.reset()
     for _ in range(args.warmup):

@@ -65,6 +65,30 @@ def check(rc):
     raise RuntimeError(msg)
 
 
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def on_device(torch, index):
+    """Context in which CUDA device `index` is current: nothing to do (and nothing paid) when it already is."""
+    return _NO_GUARD if torch.cuda.current_device() == index else torch.cuda.device(index)
+
+
+def raw_stream(torch, index):
+    """cudaStream_t (as an int) of the current torch stream on device `index`, without building a Stream object."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(index)
+    except AttributeError:  # pragma: no cover
+        return torch.cuda.current_stream(index).cuda_stream
+
+
 def require_cuda():
     import torch
     if not torch.cuda.is_available():

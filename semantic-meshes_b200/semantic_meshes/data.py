@@ -55,6 +55,17 @@ class Camera:
         self.principal_point = np.ascontiguousarray(principal_f64, dtype=np.float64).reshape(2)
         return self
 
+    def _pointers(self):
+        """Host addresses of (rotation, translation, focal_lengths, principal_point) for the C ABI; cached while the four
+        arrays are the same objects (numpy's .ctypes is slow enough to show in a loop over views)."""
+        key = (id(self.rotation), id(self.translation), id(self.focal_lengths), id(self.principal_point))
+        cached = self.__dict__.get("_ptr_cache")
+        if cached is None or cached[0] != key:
+            cached = (key, (self.rotation.ctypes.data, self.translation.ctypes.data, self.focal_lengths.ctypes.data,
+                            self.principal_point.ctypes.data))
+            self.__dict__["_ptr_cache"] = cached
+        return cached[1]
+
     def __repr__(self):
         return (f"Camera(resolution={self.resolution}, f={self.focal_lengths.tolist()}, "
                 f"c={self.principal_point.tolist()})")

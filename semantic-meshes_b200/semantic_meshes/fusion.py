@@ -48,6 +48,7 @@ class MeshAggregator:
         self._kind = _lib.KIND[name]
         self._cpad = int(_lib.lib.smesh_fuse_padded_classes(classes))
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._id_dtypes = _torch_id_dtypes(torch)
         # raw accumulator [P, Cpad] (mul: -log p), per-view pixel counters [P], flat id scratch (grown on demand)
         self._acc = torch.zeros((primitives, self._cpad), dtype=torch.float32, device=self.device)
@@ -190,7 +191,8 @@ class MeshAggregator:
         torch = self._torch
         cur = torch.cuda.current_stream(self.device)
         capturing = torch.cuda.is_current_stream_capturing()
-        others = [s for s in self._users if s != cur and self._may_wait_for(s, capturing)]
+        others = [torch.cuda.ExternalStream(h, device=self.device) for h in self._users if h != cur.cuda_stream]
+        others = [s for s in others if self._may_wait_for(s, capturing)]
         for s in others:
             cur.wait_stream(s)
         self._counts2.zero_()
@@ -198,8 +200,8 @@ class MeshAggregator:
         if others:
             self._reset_event = torch.cuda.Event()
             self._reset_event.record(cur)
-        self._reset_stream, self._reset_captured = cur, capturing
-        self._users = {cur}
+        self._reset_stream, self._reset_captured = cur.cuda_stream, capturing
+        self._users = {cur.cuda_stream}
         self._epoch = 0
         self._epoch_gen += 1
         self._array_epoch = [0, 0]
@@ -213,15 +215,16 @@ class MeshAggregator:
             return self._torch.cuda.is_current_stream_capturing()
 
     def _enter(self):
-        """Before anything that reads or writes the counters is enqueued on the current stream."""
+        """Before anything that reads or writes the counters is enqueued on the current stream (streams are tracked by
+        their raw handles: this runs once per view)."""
         torch = self._torch
-        cur = torch.cuda.current_stream(self.device)
-        if cur not in self._users:
+        h = _lib.raw_stream(torch, self._dev_index)
+        if h not in self._users:
             ev = self._reset_event
             # (an event recorded inside a capture means something only to streams of that capture)
-            if ev is not None and cur != self._reset_stream and self._reset_captured == torch.cuda.is_current_stream_capturing():
-                cur.wait_event(ev)
-            self._users.add(cur)
+            if ev is not None and h != self._reset_stream and self._reset_captured == torch.cuda.is_current_stream_capturing():
+                torch.cuda.current_stream(self.device).wait_event(ev)
+            self._users.add(h)
 
     def _counts_for(self, epoch):
         return self._counts2[epoch & 1]
@@ -273,7 +276,7 @@ class MeshAggregator:
             return
         pr, wt, n_outer, n_inner, ids_so, ids_si, w_so, w_si = lay
         npix = n_outer * n_inner
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = _lib.raw_stream(torch, self._dev_index)
         flat32 = ((ids.dtype == torch.int32 and self.primitives <= 0x7FFFFFFF) or ids.dtype == torch.uint32) \
             and (ids_si == 1 or n_inner == 1) and (ids_so == n_inner or n_outer == 1)
         token = getattr(primitive_indices, "_smesh_counted", None)
@@ -287,7 +290,7 @@ class MeshAggregator:
             epoch = token[2] if counted else self._next_epochs(npix)
             self._enter()
             epoch2 = self._next_epochs(nxt.numel())
-            with torch.cuda.device(self.device):
+            with _lib.on_device(torch, self._dev_index):
                 rc = _lib.lib.smesh_fuse_scatter_count_next(
                     self._kind, ids.data_ptr(), pr.data_ptr(), wt.data_ptr() if wt is not None else None, npix,
                     self.classes, self.primitives, self.images_equal_weight, self._counts_for(epoch).data_ptr(), epoch,
@@ -300,7 +303,7 @@ class MeshAggregator:
         if counted:
             epoch = token[2]
             self._enter()
-            with torch.cuda.device(self.device):
+            with _lib.on_device(torch, self._dev_index):
                 rc = _lib.lib.smesh_fuse_scatter(self._kind, ids.data_ptr(), pr.data_ptr(),
                                                  wt.data_ptr() if wt is not None else None, npix, self.classes,
                                                  self.primitives, self.images_equal_weight,
@@ -309,7 +312,7 @@ class MeshAggregator:
             _lib.check(rc)
             return
         epoch = self._next_epochs(npix)
-        with torch.cuda.device(self.device):
+        with _lib.on_device(torch, self._dev_index):
             rc = _lib.lib.smesh_fuse_add(self._kind, ids.data_ptr(), id_dtype, ids_so, ids_si, pr.data_ptr(),
                                          wt.data_ptr() if wt is not None else None, w_so, w_si, n_outer, n_inner,
                                          self.classes, self.primitives, self.images_equal_weight,

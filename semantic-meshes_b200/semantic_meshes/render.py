@@ -23,6 +23,7 @@ class TriangleRenderer:
             raise TypeError("render.triangles expects a semantic_meshes.data.Ply")
         self._torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         verts = np.ascontiguousarray(ply.vertices, dtype=np.float32)
         faces = np.ascontiguousarray(ply.faces, dtype=np.int32)
         if faces.size and (faces.min() < 0 or faces.max() >= verts.shape[0]):
@@ -41,6 +42,7 @@ class TriangleRenderer:
                                                         self._mesh.data_ptr(), self._mesh.numel(), temp.data_ptr(),
                                                         temp.numel(), torch.cuda.current_stream().cuda_stream))
             torch.cuda.current_stream().synchronize()  # temp / verts_d / faces_d are released on return
+        self._mesh_ptr, self._mesh_bytes = self._mesh.data_ptr(), self._mesh.numel()
         self._workspace = None
         self._workspace_res = None
 
@@ -92,22 +94,19 @@ class TriangleRenderer:
                 raise ValueError("render(count_into=...): the aggregator must hold one row per face of this mesh, on this device")
             if W * H < (1 << 24) and self._F > 0 and not capsule:
                 epoch = count_into._next_epochs(W * H)
-        with torch.cuda.device(self.device):
+        R, t, f, c = camera._pointers()
+        with _lib.on_device(torch, self._dev_index):
             ws = self._ensure_workspace(W, H)
             idx = torch.empty((W, H), dtype=torch.int32, device=self.device)
             depth = torch.empty((W, H), dtype=torch.float32, device=self.device)
-            R, t = camera.rotation, camera.translation
-            f, c = camera.focal_lengths, camera.principal_point
-            stream = torch.cuda.current_stream().cuda_stream
+            stream = _lib.raw_stream(torch, self._dev_index)
             if epoch != 0:
-                rc = _lib.lib.smesh_raster_render_counted(self._mesh.data_ptr(), self._mesh.numel(), self._V, self._F,
-                                                          R.ctypes.data, t.ctypes.data, f.ctypes.data, c.ctypes.data, W, H,
+                rc = _lib.lib.smesh_raster_render_counted(self._mesh_ptr, self._mesh_bytes, self._V, self._F, R, t, f, c, W, H,
                                                           ws.data_ptr(), ws.numel(), idx.data_ptr(), depth.data_ptr(),
                                                           count_into._counts_for(epoch).data_ptr(), epoch, stream)
             else:
-                rc = _lib.lib.smesh_raster_render(self._mesh.data_ptr(), self._mesh.numel(), self._V, self._F, R.ctypes.data,
-                                                  t.ctypes.data, f.ctypes.data, c.ctypes.data, W, H, ws.data_ptr(),
-                                                  ws.numel(), idx.data_ptr(), depth.data_ptr(), stream)
+                rc = _lib.lib.smesh_raster_render(self._mesh_ptr, self._mesh_bytes, self._V, self._F, R, t, f, c, W, H,
+                                                  ws.data_ptr(), ws.numel(), idx.data_ptr(), depth.data_ptr(), stream)
         _lib.check(rc)
         if epoch != 0:
             idx._smesh_counted = (id(count_into), count_into._epoch_gen, epoch)
@@ -169,17 +168,15 @@ class TexturedTriangleRenderer(TriangleRenderer):
         W, H = camera.resolution
         if W < 1 or H < 1:
             raise ValueError("render: empty resolution")
-        with torch.cuda.device(self.device):
+        R, t, f, c = camera._pointers()
+        with _lib.on_device(torch, self._dev_index):
             ws = self._ensure_workspace(W, H)
             idx = torch.empty((W, H), dtype=torch.int32, device=self.device)
             depth = torch.empty((W, H), dtype=torch.float32, device=self.device)
-            R, t = camera.rotation, camera.translation
-            f, c = camera.focal_lengths, camera.principal_point
-            rc = _lib.lib.smesh_raster_render_texels(self._mesh.data_ptr(), self._mesh.numel(), self._V, self._F,
-                                                     self._tri_res.data_ptr(), self._first_texel.data_ptr(), R.ctypes.data,
-                                                     t.ctypes.data, f.ctypes.data, c.ctypes.data, W, H, ws.data_ptr(),
-                                                     ws.numel(), idx.data_ptr(), depth.data_ptr(),
-                                                     torch.cuda.current_stream().cuda_stream)
+            rc = _lib.lib.smesh_raster_render_texels(self._mesh_ptr, self._mesh_bytes, self._V, self._F,
+                                                     self._tri_res.data_ptr(), self._first_texel.data_ptr(), R, t, f, c, W, H,
+                                                     ws.data_ptr(), ws.numel(), idx.data_ptr(), depth.data_ptr(),
+                                                     _lib.raw_stream(torch, self._dev_index))
         _lib.check(rc)
         if capsule:
             from torch.utils.dlpack import to_dlpack
