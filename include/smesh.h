@@ -95,7 +95,8 @@ int smesh_raster_workspace_bytes(int64_t V, int64_t F, int W, int H, size_t* byt
  *   workspace  device scratch of smesh_raster_workspace_bytes(V, F, W, H) bytes; ZERO-FILL it once after allocating it
  *           (it caches a per-pixel table keyed by the intrinsics and the cleared depth buffer) and keep it for the next
  *           views of the same mesh; one workspace serves one stream at a time
- *   idx_out uint32[W][H] (0xFFFFFFFF where nothing is hit), depth_out float32[W][H] (+inf where nothing is hit)
+ *   idx_out uint32[W][H] (0xFFFFFFFF where nothing is hit), depth_out float32[W][H] (+inf where nothing is hit; may be
+ *           NULL when the caller only fuses the view: the depth image is then not written)
  * Results are bit-identical to the reference kernel as compiled by nvcc 12.9 for sm_100a, with the one documented
  * strengthening that exact depth ties go to the lowest triangle index (the reference is order-dependent there).
  */

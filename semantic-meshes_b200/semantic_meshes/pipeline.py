@@ -5,20 +5,27 @@ being fused keeps both halves of the GPU busy. Two CUDA streams, one event per v
 also counts the view's pixels per face into the aggregator (`render(camera, count_into=aggregator)`, SURVEY 8f N2: the
 index image is not read a second time for the histogram) and `add` is the scatter stage alone; measured on cfg3 this is
 slower than counting on the fusion stream (10.2 k vs 10.8 k views/s) because the render stream is the longer of the two,
-so it is off by default. The results are identical to the sequential README loop
+so it is off by default. With group=K > 1 the views go K at a time: K renders into one index buffer on the render
+stream, then ONE `add_batch` of the group on the fusion stream (one count launch per group, the other counts ride in the
+scatter launches) while the next group renders. The results are identical to the sequential README loop
 (`idx, _ = renderer.render(cam); aggregator.add(idx, probs)`).
 """
 from . import _lib
 
 
 class ViewPipeline:
-    def __init__(self, renderer, aggregator, fused_count=False, count_ahead=False):
+    def __init__(self, renderer, aggregator, fused_count=False, count_ahead=False, write_depth=False, group=1):
         torch = _lib.require_cuda()
         self.fused_count = bool(fused_count)
         # count_ahead: the count stage of view v+1 rides in the scatter launch of view v (MeshAggregator.add(count_next=)).
         # Off by default: the fusion of view v then has to wait for the render of view v+1, the two streams fall into
         # lock step and the tail of every render runs alone - measured 11.1 k against 12.4 k views/s at config 3.
         self.count_ahead = bool(count_ahead)
+        # write_depth: materialise the depth image of every view although the pipeline has no use for it (bench.py does,
+        # so that a timed view is exactly one reference-style render() + add())
+        self.write_depth = bool(write_depth)
+        # group: views per add_batch call (1 = one add per view); needs predictions that form a regular batch in memory
+        self.group = max(1, int(group))
         self._torch = torch
         self.renderer, self.aggregator = renderer, aggregator
         with torch.cuda.device(renderer.device):
@@ -28,6 +35,10 @@ class ViewPipeline:
         """cameras: sequence of data.Camera; predictions: sequence (or batched tensor) of (W, H, C) float32 arrays, one per
         camera; weights: optional sequence of (W, H) float32. Returns the list of index images if keep_indices."""
         torch = self._torch
+        if self.group > 1 and not self.fused_count and len(cameras) > 0:
+            done = self._run_grouped(cameras, predictions, weights, keep_indices)
+            if done is not False:
+                return done
         main = torch.cuda.current_stream()
         rs = self._render_stream
         rs.wait_stream(main)  # the render stream starts after whatever produced the inputs
@@ -42,7 +53,8 @@ class ViewPipeline:
                 if fused and v >= 2:
                     rs.wait_event(added[v - 2])  # two counter arrays: view v reuses the one of view v - 2
                 with torch.cuda.stream(rs):
-                    idx, _ = self.renderer.render(cameras[v], count_into=self.aggregator if fused else None)
+                    idx, _ = self.renderer.render(cameras[v], count_into=self.aggregator if fused else None,
+                                                  depth=self.write_depth)
                     ev = torch.cuda.Event()
                     ev.record(rs)
                 nxt = (idx, ev)
@@ -65,4 +77,69 @@ class ViewPipeline:
                     kept.append(idx_prev)
             pending = nxt
         rs.wait_stream(main)  # the renderer's workspace / outputs are not reused before the last add has been enqueued
+        return kept if keep_indices else None
+
+    @staticmethod
+    def _as_batch(torch, items, first, k):
+        """items[first : first + k] as ONE (k, ...) tensor without a copy, or None: a batched tensor is sliced; a sequence of
+        tensors qualifies when its elements are equally shaped views of one storage at a constant distance."""
+        if isinstance(items, torch.Tensor):
+            return items[first:first + k]
+        a = items[first]
+        if not isinstance(a, torch.Tensor) or not a.is_cuda:
+            return None
+        if k == 1:
+            return a.unsqueeze(0)
+        step = items[first + 1].data_ptr() - a.data_ptr() if isinstance(items[first + 1], torch.Tensor) else 0
+        if step <= 0 or step % a.element_size() != 0:
+            return None
+        for j in range(1, k):
+            b = items[first + j]
+            if (not isinstance(b, torch.Tensor) or b.shape != a.shape or b.stride() != a.stride() or b.dtype != a.dtype
+                    or b.device != a.device or b.data_ptr() != a.data_ptr() + j * step
+                    or b.untyped_storage().data_ptr() != a.untyped_storage().data_ptr()):
+                return None
+        return torch.as_strided(a, (k,) + tuple(a.shape), (step // a.element_size(),) + tuple(a.stride()))
+
+    def _run_grouped(self, cameras, predictions, weights, keep_indices):
+        """K views at a time (see the module docstring). -> False if the inputs do not form regular batches."""
+        torch = self._torch
+        n, K = len(cameras), self.group
+        res = cameras[0].resolution
+        if any(c.resolution != res for c in cameras):
+            return False
+        groups = [(g, min(K, n - g)) for g in range(0, n, K)]
+        batches = []
+        for g, k in groups:
+            pb = self._as_batch(torch, predictions, g, k)
+            wb = self._as_batch(torch, weights, g, k) if weights is not None else None
+            if pb is None or (weights is not None and wb is None):
+                return False
+            batches.append((pb, wb))
+        main = torch.cuda.current_stream()
+        rs = self._render_stream
+        rs.wait_stream(main)
+        W, H = res
+        kept = []
+        pending = None
+        for gi in range(len(groups) + 1):
+            nxt = None
+            if gi < len(groups):
+                g, k = groups[gi]
+                with torch.cuda.stream(rs):
+                    buf = torch.empty((k, W, H), dtype=torch.int32, device=self.renderer.device)
+                    for j in range(k):
+                        self.renderer.render(cameras[g + j], depth=self.write_depth, out_indices=buf[j])
+                    ev = torch.cuda.Event()
+                    ev.record(rs)
+                nxt = (buf, ev, gi)
+            if pending is not None:
+                buf_prev, ev_prev, gp = pending
+                main.wait_event(ev_prev)
+                self.aggregator.add_batch(buf_prev, batches[gp][0], batches[gp][1])
+                buf_prev.record_stream(main)
+                if keep_indices:
+                    kept.extend(buf_prev[j] for j in range(buf_prev.shape[0]))
+            pending = nxt
+        rs.wait_stream(main)
         return kept if keep_indices else None

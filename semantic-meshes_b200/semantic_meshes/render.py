@@ -69,8 +69,11 @@ class TriangleRenderer:
             self._workspace_res = (W, H)
         return self._workspace
 
-    def render(self, camera, capsule=False, count_into=None):
-        """-> (primitive_indices, depth): torch tensors on the GPU, shapes (W, H).
+    def render(self, camera, capsule=False, count_into=None, depth=True, out_indices=None):
+        """-> (primitive_indices, depth): torch tensors on the GPU, shapes (W, H). depth=False (extension): the depth image
+        is not written and None is returned for it (a caller that only fuses the view saves 4 bytes per pixel of traffic).
+        out_indices (extension): a contiguous int32 (W, H) device tensor to write the index image into (a slice of a
+        batch buffer for `MeshAggregator.add_batch`).
 
         primitive_indices is int32 holding the reference's uint32 bit pattern (background 0xFFFFFFFF reads as -1; torch
         has few uint32 ops) - `MeshAggregator.add` takes it as is. With capsule=True both are returned as DLPack
@@ -97,16 +100,23 @@ class TriangleRenderer:
         R, t, f, c = camera._pointers()
         with _lib.on_device(torch, self._dev_index):
             ws = self._ensure_workspace(W, H)
-            idx = torch.empty((W, H), dtype=torch.int32, device=self.device)
-            depth = torch.empty((W, H), dtype=torch.float32, device=self.device)
+            if out_indices is None:
+                idx = torch.empty((W, H), dtype=torch.int32, device=self.device)
+            else:
+                idx = out_indices
+                if (idx.dtype != torch.int32 or tuple(idx.shape) != (W, H) or not idx.is_contiguous() or idx.device != self.device
+                        or idx.data_ptr() % 8 != 0):
+                    raise ValueError("render(out_indices=...): expected a contiguous, 8-byte aligned int32 (W, H) tensor on this device")
+            depth = torch.empty((W, H), dtype=torch.float32, device=self.device) if (depth or capsule) else None
+            depth_ptr = depth.data_ptr() if depth is not None else None
             stream = _lib.raw_stream(torch, self._dev_index)
             if epoch != 0:
                 rc = _lib.lib.smesh_raster_render_counted(self._mesh_ptr, self._mesh_bytes, self._V, self._F, R, t, f, c, W, H,
-                                                          ws.data_ptr(), ws.numel(), idx.data_ptr(), depth.data_ptr(),
+                                                          ws.data_ptr(), ws.numel(), idx.data_ptr(), depth_ptr,
                                                           count_into._counts_for(epoch).data_ptr(), epoch, stream)
             else:
                 rc = _lib.lib.smesh_raster_render(self._mesh_ptr, self._mesh_bytes, self._V, self._F, R, t, f, c, W, H,
-                                                  ws.data_ptr(), ws.numel(), idx.data_ptr(), depth.data_ptr(), stream)
+                                                  ws.data_ptr(), ws.numel(), idx.data_ptr(), depth_ptr, stream)
         _lib.check(rc)
         if epoch != 0:
             idx._smesh_counted = (id(count_into), count_into._epoch_gen, epoch)

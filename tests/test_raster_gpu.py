@@ -602,3 +602,32 @@ def test_pipeline_count_ahead_matches_sequential(sm):
     pipe.run(cams, preds)
     torch.cuda.synchronize()
     torch.testing.assert_close(ovl.state(), 2 * seq.state(), rtol=1e-5, atol=1e-6)
+
+
+def test_pipeline_grouped_matches_sequential(sm):
+    """ViewPipeline(group=K): K renders into one index buffer, one add_batch per group - with a batched prediction tensor,
+    with a list of slices of one (regular batch: no copy), with a list of separate tensors (falls back to one add per
+    view), with weights, with a view count that is not a multiple of K."""
+    import torch
+    from semantic_meshes import synthetic
+    from semantic_meshes.pipeline import ViewPipeline
+    W, H, C = 160, 120, 19
+    mesh = synthetic.mesh("terrain", 6000, seed=2)
+    renderer = sm.render.triangles(mesh)
+    P = renderer.getPrimitivesNum()
+    cams = synthetic.terrain_cameras(7, W, H, 6000, tris_per_view=1500, seed=8)
+    preds = torch.stack([synthetic.predictions_torch(W, H, C, seed=v, device="cuda") for v in range(len(cams))])
+    wts = torch.rand((len(cams), W, H), device="cuda") * 2
+    seq = sm.fusion.MeshAggregator(P, C)
+    ids_seq = []
+    for v, cam in enumerate(cams):
+        idx, _ = renderer.render(cam)
+        seq.add(idx, preds[v], wts[v])
+        ids_seq.append(idx.clone())
+    for K, pr, wt in ((3, preds, wts), (4, [preds[v] for v in range(7)], [wts[v] for v in range(7)]),
+                      (2, [preds[v].clone() for v in range(7)], [wts[v].clone() for v in range(7)])):
+        ovl = sm.fusion.MeshAggregator(P, C)
+        kept = ViewPipeline(renderer, ovl, group=K).run(cams, pr, wt, keep_indices=True)
+        torch.cuda.synchronize()
+        assert len(kept) == 7 and all(torch.equal(a, b) for a, b in zip(kept, ids_seq))
+        torch.testing.assert_close(ovl.state(), seq.state(), rtol=1e-5, atol=1e-6)
