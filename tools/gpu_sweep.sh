@@ -12,7 +12,7 @@ for setting in "$@"; do
   flags=""
   envs=""
   for tok in $setting; do
-    case $tok in --*) flags="$flags $tok";; *) envs="$envs $tok";; esac
+    case $tok in *=*) envs="$envs $tok";; *) flags="$flags $tok";; esac
   done
   env $envs timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --quick --no-parity --also "" $flags > $OUT/$name.json 2> $OUT/$name.err
   python - <<PY
