@@ -28,9 +28,9 @@ PY
 if [ "${3:-}" = "ncu" ]; then
   SMESH_PROFILE_RANGE=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 1 --warmup 3 --cycles 2 --no-graph --no-cpu-baseline --quick --also '' > $OUT/launches_bench.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'scatter_pair|count_kernel' -s 8 -c 4 -o $OUT/add_full \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:scatter_pair -s 4 -c 2 -o $OUT/add_full \
     python tools/prof_driver.py cfg3 4 > $OUT/add_full.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:raster_cluster -s 4 -c 1 -o $OUT/raster_full \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:raster_unit -s 4 -c 1 -o $OUT/raster_full \
     python tools/prof_driver.py cfg3 4 > $OUT/raster_full.log 2>&1
 fi
 ls -la $OUT
