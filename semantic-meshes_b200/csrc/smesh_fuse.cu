@@ -400,8 +400,17 @@ __device__ __forceinline__ void load_chunk(const float* __restrict__ p, int nval
 }
 
 // Shared memory: [stages][NW*32*C] floats | full[stages], empty[stages] mbarriers
+// The 128-bit row loads of the consumers (lane stride C words) are free of bank conflicts only when C / 4 is odd. For
+// C / 4 = 2 (mod 4) - C = 24, 40, 56 - lanes l and l + 4 of a quarter warp meet in the same banks, for C / 4 = 4 (mod 8) -
+// C = 48 - lanes l and l + 2: PADG = 4 / 2 shifts every group of PADG pixels by one more 16-byte chunk in shared memory
+// (the tile then arrives as one bulk copy per group, issued by the lanes of the producer warp in parallel).
+__host__ __device__ constexpr int ring_pad_group(int C)
+{
+  return (C % 8 != 0) ? 0 : ((C / 4) % 4 == 2 ? 4 : ((C / 4) % 8 == 4 ? 2 : 0));
+}
+
 // RIDER: the CTA has one more warp, which runs the next view's count stage (see ScatterArgs)
-template <int KIND, int CT, bool RIDER>
+template <int KIND, int CT, bool RIDER, int PADG>
 __global__ void __launch_bounds__(RIDER ? 320 : 288, RIDER ? 3 : 0) scatter_kernel(ScatterArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -410,7 +419,7 @@ __global__ void __launch_bounds__(RIDER ? 320 : 288, RIDER ? 3 : 0) scatter_kern
   const int al = (C % 4 == 0) ? 4 : ((C % 2 == 0) ? 2 : 1);
   const int NW = (int) (blockDim.x >> 5) - 1 - (RIDER ? 1 : 0); // consumer warps; warp 0 produces, the last one may count
   const int tile_px = NW * 32;
-  const size_t stage_floats = (size_t) tile_px * C;
+  const size_t stage_floats = (size_t) tile_px * C + (PADG > 0 ? (size_t) (tile_px / PADG) * 4 : 0);
   const int stages = a.stages;
 
   float* stage_base = reinterpret_cast<float*>(smem_raw);
@@ -430,6 +439,48 @@ __global__ void __launch_bounds__(RIDER ? 320 : 288, RIDER ? 3 : 0) scatter_kern
   }
   __syncthreads();
 
+  if (warp == 0 && PADG > 0)
+  {
+    // ===== producer, padded layout: one bulk copy per group of PADG pixels, the lanes issue them in parallel =====
+    const uint64_t policy = l2_evict_first_policy();
+    int s = 0;
+    uint32_t use_parity = 1;
+    bool first_pass = true;
+    constexpr int PG = PADG > 0 ? PADG : 1;
+    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
+    {
+      if (!first_pass)
+      {
+        if (lane == 0)
+        {
+          mbar_wait(empty_bar + s, use_parity, a.wait_hint);
+        }
+        __syncwarp();
+      }
+      const int64_t px0 = tile * tile_px;
+      const int px_n = (int) min((int64_t) tile_px, a.npix - px0);
+      float* dst = stage_base + stage_floats * s;
+      const float* src = a.probs + (size_t) px0 * C;
+      if (lane == 0)
+      {
+        mbar_arrive_expect_tx(full_bar + s, (uint32_t) ((size_t) px_n * C * 4)); // C % 8 == 0: whole 16-byte chunks
+      }
+      __syncwarp();
+      const int ngroups = (px_n + PG - 1) / PG;
+      for (int g = lane; g < ngroups; g += 32)
+      {
+        const int gp = min(PG, px_n - g * PG);
+        bulk_g2s(dst + (size_t) g * (PG * C + 4), src + (size_t) g * PG * C, (uint32_t) (gp * C * 4), full_bar + s, policy);
+      }
+      if (++s == stages)
+      {
+        s = 0;
+        first_pass = false;
+        use_parity ^= 1u;
+      }
+    }
+    return;
+  }
   if (warp == 0)
   {
     // ===== producer: one lane streams the tiles of this CTA into the ring =====
@@ -506,7 +557,7 @@ __global__ void __launch_bounds__(RIDER ? 320 : 288, RIDER ? 3 : 0) scatter_kern
 
   int s = 0;
   uint32_t parity = 0;
-  const float* stage_ptr = stage_base + (size_t) lane_px * C;
+  const float* stage_ptr = stage_base + (size_t) lane_px * C + (PADG > 0 ? (size_t) (lane_px / (PADG > 0 ? PADG : 1)) * 4 : 0);
   for (; tile < a.ntiles; tile += tile_stride)
   {
     const uint32_t id2 = load_id(tile + 2 * tile_stride);
@@ -1488,9 +1539,17 @@ static uint32_t scatter_run_cap()
   return (env == 1 || env == 2 || env == 4 || env == 8 || env == 16 || env == 32) ? (uint32_t) env : 32u;
 }
 
+static int ring_pad_group_enabled(int C)
+{
+  static const bool off = getenv("SMESH_NO_RING_PAD") != nullptr; // profiling only
+  return off ? 0 : ring_pad_group(C);
+}
+
 static size_t ring_smem_bytes(int C, const RingConfig& cfg)
 {
-  return (size_t) cfg.stages * cfg.consumer_warps * 32 * C * 4 + (size_t) cfg.stages * 16;
+  const int padg = ring_pad_group_enabled(C);
+  return (size_t) cfg.stages * (cfg.consumer_warps * 32 * C * 4 + (padg > 0 ? (cfg.consumer_warps * 32 / padg) * 16 : 0)) +
+         (size_t) cfg.stages * 16;
 }
 
 template <int KIND, int CT>
@@ -1499,7 +1558,18 @@ static int launch_scatter_ring(const ScatterArgs& args_in, const RingConfig& cfg
   ScatterArgs args = args_in;
   const size_t smem = ring_smem_bytes(args.C, cfg);
   const bool rider = args.next_ids != nullptr;
-  auto kernel = rider ? scatter_kernel<KIND, CT, true> : scatter_kernel<KIND, CT, false>;
+  // (a compile-time C knows its padding; the run-time instance carries the builds for 0 / 2 / 4)
+  const int padg = ring_pad_group_enabled(args.C);
+  void (*kernel)(ScatterArgs) = nullptr;
+  if (CT > 0)
+  {
+    constexpr int PG = CT > 0 ? ring_pad_group(CT) : 0;
+    if (padg == PG) kernel = rider ? scatter_kernel<KIND, CT, true, PG> : scatter_kernel<KIND, CT, false, PG>;
+    else kernel = rider ? scatter_kernel<KIND, CT, true, 0> : scatter_kernel<KIND, CT, false, 0>;
+  }
+  else if (padg == 4) kernel = rider ? scatter_kernel<KIND, CT, true, 4> : scatter_kernel<KIND, CT, false, 4>;
+  else if (padg == 2) kernel = rider ? scatter_kernel<KIND, CT, true, 2> : scatter_kernel<KIND, CT, false, 2>;
+  else kernel = rider ? scatter_kernel<KIND, CT, true, 0> : scatter_kernel<KIND, CT, false, 0>;
   const int threads = (cfg.consumer_warps + 1 + (rider ? 1 : 0)) * 32;
   int blocks_per_sm = 0;
   const int cfg_rc = kernel_blocks_per_sm(reinterpret_cast<const void*>(kernel), threads, smem, &blocks_per_sm);

@@ -802,3 +802,31 @@ def test_add_with_count_next_chain(sm, kind, C):
     if kind == "mul":
         exp = np.where(np.isinf(ref.acc), ref.acc, exp)
     assert_acc_close(kind, agg.state().cpu().numpy(), exp, rtol=5e-5)
+
+
+@pytest.mark.parametrize("kind,C", [("summax", 8), ("summax", 16), ("sum", 24), ("mul", 24), ("sum", 32), ("sum", 48), ("summax", 48),
+                                    ("sum", 56), ("sum", 44)])
+def test_ring_kernel_padded_layouts(sm, kind, C):
+    """The ring kernel pads its shared-memory tile for class counts whose 128-bit row loads would collide in the banks
+    (C = 8, 24, 40, 56: every 4 pixels; C = 16, 48: every 2): ragged images, tiles that end inside a group, batches with
+    the riding count, against the oracle."""
+    import torch
+    W, H, P = 53, 77, 250
+    rng = np.random.default_rng(C * 13 + len(kind))
+    agg = sm.fusion.MeshAggregator(primitives=P, classes=C, aggregator=kind)
+    ref = oracle.Aggregator(P, C, kind)
+    views = []
+    for v in range(3):
+        ids, probs = make_view(rng, W, H, C, P, block=(1, 2, 6)[v])
+        wts = (rng.random((W, H)) * 2).astype(np.float32) if v == 1 else None
+        agg.add(torch.from_numpy(ids.view(np.int32)).cuda(), torch.from_numpy(probs).cuda(),
+                None if wts is None else torch.from_numpy(wts).cuda())
+        ref.add(ids, probs, wts)
+        views.append((ids, probs))
+    ids_b = torch.from_numpy(np.stack([v[0] for v in views]).view(np.int32)).cuda()
+    probs_b = torch.from_numpy(np.stack([v[1] for v in views])).cuda()
+    agg.add_batch(ids_b, probs_b)
+    for i, p in views:
+        ref.add(i, p)
+    assert_acc_close(kind, agg.state().cpu().numpy(), ref.acc)
+    assert_get_close(kind, agg.get(), ref.get())
