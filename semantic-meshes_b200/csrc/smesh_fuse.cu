@@ -741,6 +741,16 @@ __global__ void __launch_bounds__(RIDER ? 320 : 288, RIDER ? 3 : 0) scatter_kern
 
 // LEAN: compiled for 8 CTAs of <= 3 consumer warps per SM (64 registers instead of 84, 24 bytes of spills): leaves room
 // for more rasterizer CTAs next to it. Opt-in (SMESH_PAIR_LEAN=1, C = 19), not measured yet.
+// Bank conflicts of the lanes' row loads (lane stride 2 C words). Odd C: 64-bit loads, conflict free. C = 2 (mod 4): the 2 C
+// floats of a lane are whole 16-byte chunks and 128-bit loads are conflict free. C = 0 (mod 4): 128-bit loads, and every
+// group of PADL lanes is shifted by one more 16-byte chunk in shared memory (C = 4, 12, 20: lanes l and l + 4 would meet
+// in the same banks, C = 8: l and l + 2, C = 16: all of them); the tile then arrives as one bulk copy per group, issued by
+// the lanes of the producer warp in parallel. (Round 1: C = 16 ran at a third of the roofline, 16-way conflicts.)
+__host__ __device__ constexpr int pair_pad_lanes(int C)
+{
+  return (C % 4 != 0) ? 0 : (C % 8 == 4 ? 4 : (C % 16 == 8 ? 2 : 1));
+}
+
 template <int KIND, int CT, bool LEAN = false>
 __global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LEAN ? 64 : 88) scatter_pair_kernel(ScatterArgs a)
 {
@@ -748,11 +758,12 @@ __global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LE
   constexpr int C = CT;
   constexpr int Cpad = (CT + 3) & ~3;
   constexpr int NCHUNK = Cpad / 4;
+  constexpr int PADL = pair_pad_lanes(CT);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const bool has_count = a.next_ids != nullptr;
   const int NW = (int) (blockDim.x >> 5) - 1 - (has_count ? 1 : 0); // consumer warps (warp 0 produces, the last may count)
   const int tile_px = NW * 64;
-  const size_t stage_floats = (size_t) tile_px * C;
+  const size_t stage_floats = (size_t) tile_px * C + (PADL > 0 ? (size_t) (NW * 32 / (PADL > 0 ? PADL : 1)) * 4 : 0);
   const int stages = a.stages;
 
   float* stage_base = reinterpret_cast<float*>(smem_raw);
@@ -773,6 +784,48 @@ __global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LE
   }
   __syncthreads();
 
+  if (warp == 0 && PADL > 0)
+  {
+    // ===== producer, padded layout: one bulk copy per group of PADL lanes (2 PADL pixels), issued by the lanes in parallel =====
+    const uint64_t policy = l2_evict_first_policy();
+    constexpr int GP = 2 * (PADL > 0 ? PADL : 1); // pixels per group
+    int s = 0;
+    uint32_t use_parity = 1;
+    bool first_pass = true;
+    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
+    {
+      if (!first_pass)
+      {
+        if (lane == 0)
+        {
+          mbar_wait(empty_bar + s, use_parity, a.wait_hint);
+        }
+        __syncwarp();
+      }
+      const int64_t px0 = tile * tile_px;
+      const int px_n = (int) min((int64_t) tile_px, a.npix - px0);
+      float* dst = stage_base + stage_floats * s;
+      const float* src = a.probs + (size_t) px0 * C;
+      if (lane == 0)
+      {
+        mbar_arrive_expect_tx(full_bar + s, (uint32_t) ((size_t) px_n * C * 4)); // C % 4 == 0: whole 16-byte chunks
+      }
+      __syncwarp();
+      const int ngroups = (px_n + GP - 1) / GP;
+      for (int g = lane; g < ngroups; g += 32)
+      {
+        const int gp = min(GP, px_n - g * GP);
+        bulk_g2s(dst + (size_t) g * (GP * C + 4), src + (size_t) g * GP * C, (uint32_t) (gp * C * 4), full_bar + s, policy);
+      }
+      if (++s == stages)
+      {
+        s = 0;
+        first_pass = false;
+        use_parity ^= 1u;
+      }
+    }
+    return;
+  }
   if (warp == 0)
   {
     if (lane == 0)
@@ -859,7 +912,7 @@ __global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LE
 
   int s = 0;
   uint32_t parity = 0;
-  const float* stage_ptr = stage_base + (size_t) lane_px * C;
+  const float* stage_ptr = stage_base + (size_t) lane_px * C + (PADL > 0 ? (size_t) ((cw * 32 + lane) / (PADL > 0 ? PADL : 1)) * 4 : 0);
   for (; tile < a.ntiles; tile += tile_stride)
   {
     const uint2 id2 = load_ids(tile + 2 * tile_stride);
@@ -867,15 +920,31 @@ __global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LE
     const uint2 n1 = make_uint2(load_n(id1.x), load_n(id1.y));
 
     mbar_wait(full_bar + s, parity, a.wait_hint);
-    const float2* row2 = reinterpret_cast<const float2*>(stage_ptr + stage_floats * s);
-    // ---- both pixels' class vectors: 2C contiguous floats, C 64-bit loads ----
+    // ---- both pixels' class vectors: 2C contiguous floats, C 64-bit loads (even C: C / 2 128-bit loads) ----
     float ab[2 * C];
-#pragma unroll
-    for (int k = 0; k < C; k++)
+    if constexpr (C % 2 == 0)
     {
-      const float2 t = row2[k];
-      ab[2 * k] = t.x;
-      ab[2 * k + 1] = t.y;
+      const float4* row4 = reinterpret_cast<const float4*>(stage_ptr + stage_floats * s);
+#pragma unroll
+      for (int k = 0; k < C / 2; k++)
+      {
+        const float4 t = row4[k];
+        ab[4 * k] = t.x;
+        ab[4 * k + 1] = t.y;
+        ab[4 * k + 2] = t.z;
+        ab[4 * k + 3] = t.w;
+      }
+    }
+    else
+    {
+      const float2* row2 = reinterpret_cast<const float2*>(stage_ptr + stage_floats * s);
+#pragma unroll
+      for (int k = 0; k < C; k++)
+      {
+        const float2 t = row2[k];
+        ab[2 * k] = t.x;
+        ab[2 * k + 1] = t.y;
+      }
     }
     float A[Cpad], B[Cpad];
 #pragma unroll
@@ -1627,7 +1696,9 @@ static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
       return launch_scatter_pair<KIND, CT == 19 ? 19 : 2, CT == 19>(args_in, stream);
     }
   }
-  const size_t smem = (size_t) cfg.stages * cfg.consumer_warps * 64 * CT * 4 + (size_t) cfg.stages * 16 +
+  constexpr int padl = pair_pad_lanes(CT);
+  const size_t smem = (size_t) cfg.stages * (cfg.consumer_warps * 64 * CT * 4 + (padl > 0 ? (cfg.consumer_warps * 32 / padl) * 16 : 0)) +
+                      (size_t) cfg.stages * 16 +
                       (size_t) cfg.consumer_warps * (64 * ((CT + 3) & ~3) + 64) * 4; // flush rows + their face ids
   auto kernel = scatter_pair_kernel<KIND, CT, LEAN>;
   const int threads = (cfg.consumer_warps + 1 + (args.next_ids != nullptr ? 1 : 0)) * 32;
