@@ -751,14 +751,15 @@ __host__ __device__ constexpr int pair_pad_lanes(int C)
   return (C % 4 != 0) ? 0 : (C % 8 == 4 ? 4 : (C % 16 == 8 ? 2 : 1));
 }
 
-template <int KIND, int CT, bool LEAN = false>
+// WIDE: the even-C layout (128-bit loads, padded groups); false = 64-bit loads of the dense tile for every C
+template <int KIND, int CT, bool LEAN = false, bool WIDE = true>
 __global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LEAN ? 64 : 88) scatter_pair_kernel(ScatterArgs a)
 {
   static_assert(CT >= 1 && CT <= CH, "pair kernel holds 2 x Cpad values in registers");
   constexpr int C = CT;
   constexpr int Cpad = (CT + 3) & ~3;
   constexpr int NCHUNK = Cpad / 4;
-  constexpr int PADL = pair_pad_lanes(CT);
+  constexpr int PADL = WIDE ? pair_pad_lanes(CT) : 0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const bool has_count = a.next_ids != nullptr;
   const int NW = (int) (blockDim.x >> 5) - 1 - (has_count ? 1 : 0); // consumer warps (warp 0 produces, the last may count)
@@ -922,7 +923,7 @@ __global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LE
     mbar_wait(full_bar + s, parity, a.wait_hint);
     // ---- both pixels' class vectors: 2C contiguous floats, C 64-bit loads (even C: C / 2 128-bit loads) ----
     float ab[2 * C];
-    if constexpr (C % 2 == 0)
+    if constexpr (C % 2 == 0 && WIDE)
     {
       const float4* row4 = reinterpret_cast<const float4*>(stage_ptr + stage_floats * s);
 #pragma unroll
@@ -1683,6 +1684,12 @@ static PairConfig pair_config(int C)
   return cfg;
 }
 
+// measured per class count (profiles/r02s_pair_even_class_counts.txt)
+static bool pair_wide_default(int C)
+{
+  return C == 20 || C == 16 || C == 12;
+}
+
 template <int KIND, int CT, bool LEAN = false>
 static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
 {
@@ -1696,11 +1703,18 @@ static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
       return launch_scatter_pair<KIND, CT == 19 ? 19 : 2, CT == 19>(args_in, stream);
     }
   }
-  constexpr int padl = pair_pad_lanes(CT);
+  // even C: which layout (see scatter_pair_kernel); SMESH_PAIR_WIDE=0 / 1 overrides the per-C choice (tuning)
+  static const int env_wide = getenv("SMESH_PAIR_WIDE") ? atoi(getenv("SMESH_PAIR_WIDE")) : -1;
+  const bool wide = CT % 2 == 0 && !LEAN && (env_wide >= 0 ? env_wide != 0 : pair_wide_default(CT));
+  const int padl = wide ? pair_pad_lanes(CT) : 0;
   const size_t smem = (size_t) cfg.stages * (cfg.consumer_warps * 64 * CT * 4 + (padl > 0 ? (cfg.consumer_warps * 32 / padl) * 16 : 0)) +
                       (size_t) cfg.stages * 16 +
                       (size_t) cfg.consumer_warps * (64 * ((CT + 3) & ~3) + 64) * 4; // flush rows + their face ids
-  auto kernel = scatter_pair_kernel<KIND, CT, LEAN>;
+  void (*kernel)(ScatterArgs) = scatter_pair_kernel<KIND, CT, LEAN, false>;
+  if constexpr (CT % 2 == 0 && !LEAN)
+  {
+    if (wide) kernel = scatter_pair_kernel<KIND, CT, LEAN, true>;
+  }
   const int threads = (cfg.consumer_warps + 1 + (args.next_ids != nullptr ? 1 : 0)) * 32;
   int blocks_per_sm = 0;
   const int cfg_rc = kernel_blocks_per_sm(reinterpret_cast<const void*>(kernel), threads, smem, &blocks_per_sm);

@@ -22,18 +22,18 @@ tag = "ring" if os.environ.get("SMESH_NO_PAIR") else "pair"
 for C in classes:
     agg = semantic_meshes.fusion.MeshAggregator(P, C)
     probs = [synthetic.predictions_torch(W, H, C, seed=b, device="cuda") for b in range(B)]
-    ev = []
-    for rep in range(reps + 1):
-        agg.restart_epochs()
+    agg.restart_epochs()
+    counts = torch.zeros((B, P), dtype=torch.int32, device="cuda")
+    for b in range(B):
+        _lib.check(_lib.lib.smesh_fuse_count(ids[b].data_ptr(), _lib.ID_I32, H, 1, W, H, P, counts[b].data_ptr(), b + 1, None, stream))
+
+    def scatter_all():
+        s = torch.cuda.current_stream().cuda_stream
         for b in range(B):
-            _lib.check(_lib.lib.smesh_fuse_count(ids[b].data_ptr(), _lib.ID_I32, H, 1, W, H, P, agg._counts.data_ptr(), b + 1, None, stream))
-            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-            e0.record()
-            _lib.check(_lib.lib.smesh_fuse_scatter(0, ids[b].data_ptr(), probs[b].data_ptr(), None, W * H, C, P, 0.5, agg._counts.data_ptr(), b + 1, agg._acc.data_ptr(), stream))
-            e1.record()
-            if rep > 0:
-                ev.append((e0, e1))
-    torch.cuda.synchronize()
-    t = np.array([a.elapsed_time(b) for a, b in ev]) * 1e3
-    print(f"C={C:3d} {tag}: scatter median {np.median(t):.1f} us (min {t.min():.1f}); input {(4 * W * H * (C + 1)) / np.median(t) / 1e3:.0f} GB/s", flush=True)
+            _lib.check(_lib.lib.smesh_fuse_scatter(0, ids[b].data_ptr(), probs[b].data_ptr(), None, W * H, C, P, 0.5, counts[b].data_ptr(), b + 1, agg._acc.data_ptr(), s))
+
+    t = bench.timed_graph(torch, scatter_all, reps) / B * 1e3   # launches back to back in a CUDA graph
+    wide = os.environ.get("SMESH_PAIR_WIDE", "default")
+    print(f"C={C:3d} {tag} wide={wide}: scatter {t:.1f} us per launch; input {(4 * W * H * (C + 1)) / t / 1e3:.0f} GB/s", flush=True)
+    del counts
     del agg, probs
