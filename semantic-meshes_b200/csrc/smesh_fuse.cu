@@ -1684,10 +1684,13 @@ static PairConfig pair_config(int C)
   return cfg;
 }
 
-// measured per class count (profiles/r02s_pair_even_class_counts.txt)
-static bool pair_wide_default(int C)
+// Which class counts take the padded layout: measured (profiles/r02s_pair_even_class_counts.txt, cfg3's index images,
+// launches back to back): C = 12: 30.1 -> 26.8 us, C = 20: 40.7 -> 39.0 us. Not taken: C = 4, 8, 16 - their groups are bulk
+// copies of 128 bytes, and that many small copies cost more than the conflicts (17.5 -> 22.7, 26.4 -> 38.3, 58.2 -> 66.8 us);
+// C = 2 (mod 4): 128-bit loads alone change nothing (the kernel is not bound by the conflicts there).
+constexpr bool pair_wide_default(int C)
 {
-  return C == 20 || C == 16 || C == 12;
+  return C == 20 || C == 12;
 }
 
 template <int KIND, int CT, bool LEAN = false>
@@ -1703,15 +1706,15 @@ static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
       return launch_scatter_pair<KIND, CT == 19 ? 19 : 2, CT == 19>(args_in, stream);
     }
   }
-  // even C: which layout (see scatter_pair_kernel); SMESH_PAIR_WIDE=0 / 1 overrides the per-C choice (tuning)
+  // C = 12, 20: the padded layout (see scatter_pair_kernel); SMESH_PAIR_WIDE=0 switches it off (tuning)
   static const int env_wide = getenv("SMESH_PAIR_WIDE") ? atoi(getenv("SMESH_PAIR_WIDE")) : -1;
-  const bool wide = CT % 2 == 0 && !LEAN && (env_wide >= 0 ? env_wide != 0 : pair_wide_default(CT));
+  const bool wide = pair_wide_default(CT) && !LEAN && env_wide != 0;
   const int padl = wide ? pair_pad_lanes(CT) : 0;
   const size_t smem = (size_t) cfg.stages * (cfg.consumer_warps * 64 * CT * 4 + (padl > 0 ? (cfg.consumer_warps * 32 / padl) * 16 : 0)) +
                       (size_t) cfg.stages * 16 +
                       (size_t) cfg.consumer_warps * (64 * ((CT + 3) & ~3) + 64) * 4; // flush rows + their face ids
   void (*kernel)(ScatterArgs) = scatter_pair_kernel<KIND, CT, LEAN, false>;
-  if constexpr (CT % 2 == 0 && !LEAN)
+  if constexpr (pair_wide_default(CT) && !LEAN)
   {
     if (wide) kernel = scatter_pair_kernel<KIND, CT, LEAN, true>;
   }
