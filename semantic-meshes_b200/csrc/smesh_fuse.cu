@@ -404,9 +404,13 @@ __device__ __forceinline__ void load_chunk(const float* __restrict__ p, int nval
 // C / 4 = 2 (mod 4) - C = 24, 40, 56 - lanes l and l + 4 of a quarter warp meet in the same banks, for C / 4 = 4 (mod 8) -
 // C = 48 - lanes l and l + 2: PADG = 4 / 2 shifts every group of PADG pixels by one more 16-byte chunk in shared memory
 // (the tile then arrives as one bulk copy per group, issued by the lanes of the producer warp in parallel).
+// Only where a group is a bulk copy of at least 512 bytes (C = 40: 640, C = 56: 896): many smaller copies cost more than
+// the conflicts they remove (measured on the pair kernel, profiles/r02s_pair_even_class_counts.txt). C = 40 (cfg2):
+// 22.2 -> 20.1 us per view.
 __host__ __device__ constexpr int ring_pad_group(int C)
 {
-  return (C % 8 != 0) ? 0 : ((C / 4) % 4 == 2 ? 4 : ((C / 4) % 8 == 4 ? 2 : 0));
+  const int g = (C % 8 != 0) ? 0 : ((C / 4) % 4 == 2 ? 4 : ((C / 4) % 8 == 4 ? 2 : 0));
+  return g * C * 4 >= 512 ? g : 0;
 }
 
 // RIDER: the CTA has one more warp, which runs the next view's count stage (see ScatterArgs)
