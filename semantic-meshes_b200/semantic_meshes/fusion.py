@@ -191,7 +191,8 @@ class MeshAggregator:
         torch = self._torch
         cur = torch.cuda.current_stream(self.device)
         capturing = torch.cuda.is_current_stream_capturing()
-        others = [torch.cuda.ExternalStream(h, device=self.device) for h in self._users if h != cur.cuda_stream]
+        others = [torch.cuda.default_stream(self.device) if h == 0 else torch.cuda.ExternalStream(h, device=self.device)
+                  for h in self._users if h != cur.cuda_stream]
         others = [s for s in others if self._may_wait_for(s, capturing)]
         for s in others:
             cur.wait_stream(s)

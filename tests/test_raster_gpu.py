@@ -631,3 +631,23 @@ def test_pipeline_grouped_matches_sequential(sm):
         torch.cuda.synchronize()
         assert len(kept) == 7 and all(torch.equal(a, b) for a, b in zip(kept, ids_seq))
         torch.testing.assert_close(ovl.state(), seq.state(), rtol=1e-5, atol=1e-6)
+
+
+def test_render_into_buffer_and_without_depth(sm):
+    """render(camera, out_indices=slice of a batch buffer, depth=False): same index image, no depth image."""
+    import torch
+    from semantic_meshes import synthetic
+    mesh = synthetic.mesh("terrain", 8000, seed=1)
+    renderer = sm.render.triangles(mesh)
+    cams = synthetic.terrain_cameras(3, 320, 200, 8000, tris_per_view=3000, seed=2)
+    buf = torch.full((3, 320, 200), 7, dtype=torch.int32, device="cuda")
+    for j, cam in enumerate(cams):
+        ref_idx, ref_depth = renderer.render(cam)
+        idx, depth = renderer.render(cam, depth=False, out_indices=buf[j])
+        assert depth is None and idx.data_ptr() == buf[j].data_ptr() and torch.equal(buf[j], ref_idx)
+        idx2, depth2 = renderer.render(cam, out_indices=buf[j])
+        assert torch.equal(depth2.view(torch.int32), ref_depth.view(torch.int32))
+    with pytest.raises(ValueError):
+        renderer.render(cams[0], out_indices=buf[0].t())
+    with pytest.raises(ValueError):
+        renderer.render(cams[0], out_indices=torch.zeros((320, 200), dtype=torch.int64, device="cuda"))
