@@ -88,7 +88,8 @@ class MeshAggregator:
         if t.device != self.device:
             if what == "probs" and t.device.type == "cpu" and t.is_contiguous() and not torch.cuda.is_current_stream_capturing():
                 return self._upload_probs(t)
-            t = t.to(self.device, non_blocking=True)
+            # (a pinned source stays in use until the copy has run: wait for it unless the caller opted out)
+            t = t.to(self.device, non_blocking=self.async_host_inputs or not (t.device.type == "cpu" and t.is_pinned()))
         return t
 
     def _upload_probs(self, host):
