@@ -108,11 +108,14 @@ __device__ __forceinline__ uint32_t sanitize_id(int64_t raw, int64_t P)
   return (raw >= 0 && raw < P) ? (uint32_t) raw : INVALID_ID;
 }
 
-// Variant A (SMESH_COUNT_VARIANT=0, the default): flat order, 4 independent 32-pixel groups per warp iteration, runs of equal ids inside
-// a group merged by ballot into one pair of reductions.
+// Flat order, 4 independent 32-pixel groups per warp iteration, runs of equal ids inside a group merged by ballot into one
+// pair of reductions. The stage is bound by launch + load latency, not by its reductions (1.38 M per cfg3 view): without
+// any reduction it still takes 5.4 of its 8.3 us. Folding the runs of a face across 2 / 4 / 8 adjacent columns in
+// registers halved the L2 reduction sectors but doubled the instructions and was slower (10 - 11 us; round 2,
+// profiles/r02b_count_variants.txt), like round 1's per-CTA shared-memory hash (12 - 14 us).
 constexpr int COUNT_UNROLL = 4; // independent 32-pixel groups per warp iteration (loads in flight per lane)
 
-template <typename IdT, bool ATOMICS, int UNROLL>
+template <typename IdT, int UNROLL>
 __global__ void __launch_bounds__(256) count_runs_kernel(const IdT* __restrict__ ids, int64_t stride_outer, int64_t stride_inner,
                                                          int64_t n_inner, int64_t npix, int64_t P, uint32_t* __restrict__ counts,
                                                          uint32_t* __restrict__ ids32, int flat, uint32_t epoch)
@@ -156,122 +159,11 @@ __global__ void __launch_bounds__(256) count_runs_kernel(const IdT* __restrict__
       {
         const uint32_t above = headmask & ~((2u << lane) - 1u);
         const int next = above ? (__ffs(above) - 1) : 32;
-        if (ATOMICS)
+        if (epoch != 0)
         {
-          if (epoch != 0)
-          {
-            atomicMax(counts + id[k], tag);
-          }
-          atomicAdd(counts + id[k], (uint32_t) (next - lane));
+          atomicMax(counts + id[k], tag);
         }
-        else if (next == 77)
-        {
-          counts[0] = 1; // keeps the loads alive
-        }
-      }
-    }
-  }
-}
-
-// Variant B (SMESH_COUNT_VARIANT=1..3, measured slower, kept for the record): a warp counts a BLOCK of the image: COLS consecutive outer indices (image columns) x 32 consecutive
-// inner ones (rows), lane = row. Inside a column, runs of equal ids are found by ballot (one length per run head). A face
-// covers a few adjacent columns at overlapping rows, so the run of a face in column k+1 is then folded into its run in
-// column k (right to left, lengths travel by shuffle): one pair of reductions per face and block instead of one per
-// face and column.
-template <typename IdT, int COLS, bool ATOMICS>
-__global__ void __launch_bounds__(256) count_kernel(const IdT* __restrict__ ids, int64_t stride_outer, int64_t stride_inner,
-                                                    int64_t n_outer, int64_t n_inner, int64_t P, uint32_t* __restrict__ counts,
-                                                    uint32_t* __restrict__ ids32, uint32_t epoch)
-{
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
-  const uint32_t tag = epoch << COUNT_BITS;
-  const int64_t nib = (n_inner + 31) >> 5;                                 // blocks along the inner axis
-  const int64_t nblocks = nib * ((n_outer + COLS - 1) / COLS);
-  const uint32_t ge_lane = ~((1u << lane) - 1u);                           // lanes >= this one
-  for (int64_t blk = warp_global; blk < nblocks; blk += nwarps)
-  {
-    const int64_t ob = blk / nib, ib = blk - ob * nib;
-    const int64_t in = ib * 32 + lane;
-    uint32_t id[COLS];
-#pragma unroll
-    for (int k = 0; k < COLS; k++)
-    {
-      const int64_t o = ob * COLS + k;
-      id[k] = INVALID_ID;
-      if (o < n_outer && in < n_inner)
-      {
-        id[k] = sanitize_id(ids[o * stride_outer + in * stride_inner], P);
-        if (ids32 != nullptr)
-        {
-          ids32[o * n_inner + in] = id[k];
-        }
-      }
-    }
-    // runs inside each column: head lanes hold the run length; rng[k] = the rows of the run this lane heads
-    uint32_t len[COLS], headmask[COLS], rng[COLS];
-#pragma unroll
-    for (int k = 0; k < COLS; k++)
-    {
-      const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, id[k], 1);
-      const bool head = (lane == 0) || (prev != id[k]);
-      headmask[k] = __ballot_sync(0xFFFFFFFFu, head);
-      const uint32_t above = headmask[k] & ~((2u << lane) - 1u);
-      const int next = above ? (__ffs(above) - 1) : 32;
-      rng[k] = ge_lane & (above ? ((1u << next) - 1u) : 0xFFFFFFFFu);
-      len[k] = (head && id[k] != INVALID_ID) ? (uint32_t) (next - lane) : 0u;
-    }
-    // fold column k+1 into column k: the run of column k+1 that shares a row and the id with a run of column k moves its
-    // (already folded) length there. A run picks its partner through the LOWEST shared row, on both sides; the move
-    // happens only when the two picks agree, so a length moves at most once and to one place (a face split by an occluder
-    // has several runs per column: the leftovers keep their own reductions).
-#pragma unroll
-    for (int k = COLS - 2; k >= 0; k--)
-    {
-      const uint32_t eq = __ballot_sync(0xFFFFFFFFu, id[k] == id[k + 1] && id[k] != INVALID_ID);
-      int want = -1, pref = -1;
-      if (len[k] != 0u && (eq & rng[k]) != 0u)
-      {
-        const int r = __ffs(eq & rng[k]) - 1;
-        want = 31 - __clz(headmask[k + 1] & ((2u << r) - 1u)); // head of the run of column k+1 that holds row r
-      }
-      if (len[k + 1] != 0u && (eq & rng[k + 1]) != 0u)
-      {
-        const int r = __ffs(eq & rng[k + 1]) - 1;
-        pref = 31 - __clz(headmask[k] & ((2u << r) - 1u));     // head of the run of column k that holds row r
-      }
-      const int src = want >= 0 ? want : 0;
-      const int partner_pref = __shfl_sync(0xFFFFFFFFu, pref, src);
-      const uint32_t moved = __shfl_sync(0xFFFFFFFFu, len[k + 1], src);
-      const bool take = want >= 0 && partner_pref == lane;
-      const uint32_t consumed = __reduce_or_sync(0xFFFFFFFFu, take ? (1u << want) : 0u);
-      if (take)
-      {
-        len[k] += moved;
-      }
-      if ((consumed >> lane) & 1u)
-      {
-        len[k + 1] = 0u;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < COLS; k++)
-    {
-      if (len[k] != 0u)
-      {
-        if (ATOMICS)
-        {
-          if (epoch != 0)
-          {
-            atomicMax(counts + id[k], tag);
-          }
-          atomicAdd(counts + id[k], len[k]);
-        }
-        else if (len[k] == 7777u)
-        {
-          counts[0] = 1;
-        }
+        atomicAdd(counts + id[k], (uint32_t) (next - lane));
       }
     }
   }
@@ -1798,49 +1690,17 @@ static int launch_scatter(const ScatterArgs& args, cudaStream_t stream)
   return SMESH_OK;
 }
 
-// SMESH_COUNT_VARIANT (tuning / profiling): 0 = flat runs (default); 1 / 2 / 3 = blocks of 8 / 4 / 2 columns with runs folded
-// across columns; 10 / 11 = variants 0 / 1 without their reductions (the floor of the id traffic and the bookkeeping).
-// Measured on cfg3 (profiles/r02b_count_variants.txt): folding halves the reductions (1.38 M -> 0.64 M L2 sectors) but
-// doubles the instructions and is slower (11.3 vs 8.3 us): the stage is bound by launch + load latency (5.4 us without
-// any reduction), not by the reductions.
-static int count_variant()
-{
-  const char* e = getenv("SMESH_COUNT_VARIANT");
-  return e ? atoi(e) : 0;
-}
-
 template <typename IdT>
 static int launch_count(const void* ids, int64_t so, int64_t si, int64_t n_outer, int64_t n_inner, int64_t P, uint32_t* counts,
                         uint32_t* ids32, uint32_t epoch, cudaStream_t stream)
 {
-  const int variant = count_variant();
-  const IdT* p = static_cast<const IdT*>(ids);
   const int64_t npix = n_outer * n_inner;
-  const int64_t cap = (int64_t) num_sms() * 8;
-  if (variant == 0 || variant == 10)
-  {
-    const bool flat = (si == 1 || n_inner == 1) && (so == n_inner || n_outer == 1);
-    const int64_t per_block = (256 / 32) * 32 * COUNT_UNROLL;
-    int64_t blocks = std::min((npix + per_block - 1) / per_block, cap);
-    if (variant == 0)
-      count_runs_kernel<IdT, true, COUNT_UNROLL><<<(unsigned) blocks, 256, 0, stream>>>(p, so, si, n_inner, npix, P, counts, ids32, flat ? 1 : 0, epoch);
-    else
-      count_runs_kernel<IdT, false, COUNT_UNROLL><<<(unsigned) blocks, 256, 0, stream>>>(p, so, si, n_inner, npix, P, counts, ids32, flat ? 1 : 0, epoch);
-    SMESH_LAUNCH_CHECK("count_runs_kernel");
-    return SMESH_OK;
-  }
-  const int cols = variant == 2 ? 4 : (variant == 3 ? 2 : 8);
-  const int64_t items = ((n_inner + 31) / 32) * ((n_outer + cols - 1) / cols); // one warp each
-  const int64_t blocks = std::min((items + 7) / 8, cap);
-  if (variant == 11)
-    count_kernel<IdT, 8, false><<<(unsigned) blocks, 256, 0, stream>>>(p, so, si, n_outer, n_inner, P, counts, ids32, epoch);
-  else if (cols == 8)
-    count_kernel<IdT, 8, true><<<(unsigned) blocks, 256, 0, stream>>>(p, so, si, n_outer, n_inner, P, counts, ids32, epoch);
-  else if (cols == 4)
-    count_kernel<IdT, 4, true><<<(unsigned) blocks, 256, 0, stream>>>(p, so, si, n_outer, n_inner, P, counts, ids32, epoch);
-  else
-    count_kernel<IdT, 2, true><<<(unsigned) blocks, 256, 0, stream>>>(p, so, si, n_outer, n_inner, P, counts, ids32, epoch);
-  SMESH_LAUNCH_CHECK("count_kernel");
+  const bool flat = (si == 1 || n_inner == 1) && (so == n_inner || n_outer == 1);
+  const int64_t per_block = (256 / 32) * 32 * COUNT_UNROLL;
+  const int64_t blocks = std::min((npix + per_block - 1) / per_block, (int64_t) num_sms() * 8);
+  count_runs_kernel<IdT, COUNT_UNROLL><<<(unsigned) blocks, 256, 0, stream>>>(static_cast<const IdT*>(ids), so, si, n_inner, npix, P,
+                                                                             counts, ids32, flat ? 1 : 0, epoch);
+  SMESH_LAUNCH_CHECK("count_runs_kernel");
   return SMESH_OK;
 }
 
