@@ -380,7 +380,7 @@ def run_ours(args, cfg):
         parity = check_parity(scene, kinds=("sum", "summax", "mul") if rank == 0 else ("sum",))
     agg = semantic_meshes.fusion.MeshAggregator(primitives=P, classes=C)
     pipe = ViewPipeline(renderer, agg, fused_count=args.fused_count, count_ahead=args.count_ahead, write_depth=True,
-                        group=args.group)
+                        group=args.group, count_stream=args.count_stream)
     strong = args.scaling == "strong"
     if strong:
         # the config's own job: cfg["views"] views dealt round-robin; a rank cycles its B resident views to make up its share
@@ -792,6 +792,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="render and add strictly one after the other on one stream")
     ap.add_argument("--fused-count", action="store_true", help="count the view's pixels per face in the render pass (N2)")
     ap.add_argument("--count-ahead", action="store_true", help="pipeline: the count of view v+1 rides in the scatter of view v")
+    ap.add_argument("--count-stream", action="store_true", help="pipeline: the count stage on a third stream")
     ap.add_argument("--group", type=int, default=1, help="pipeline: views per add_batch call (1 = one add per view)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity checks (profiling runs only)")

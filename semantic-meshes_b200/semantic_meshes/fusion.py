@@ -323,6 +323,25 @@ class MeshAggregator:
         self._release_stage()
         _lib.check(rc)
 
+    def precount(self, primitive_indices):
+        """Extension: take the per-face pixel counts of an index image NOW, on the current stream (the count stage of
+        `add` as a call of its own); the `add` of that image then runs its scatter stage only. For callers that can spare a
+        stream: the count stage is bound by latency, not by throughput, and overlaps with anything. Returns False (and
+        does nothing) if the image cannot be counted ahead (not a flat int32 / uint32 device image below 2^24 pixels, or
+        the 8-bit epoch is about to wrap)."""
+        torch = self._torch
+        t = self._rider_candidate(primitive_indices)
+        if t is None or self.primitives == 0 or self._epoch + 1 > 255:
+            return False
+        epoch = self._next_epochs(t.numel())
+        with _lib.on_device(torch, self._dev_index):
+            rc = _lib.lib.smesh_fuse_count(t.data_ptr(), _lib.ID_U32 if t.dtype == torch.uint32 else _lib.ID_I32, t.shape[1], 1,
+                                           t.shape[0], t.shape[1], self.primitives, self._counts_for(epoch).data_ptr(), epoch,
+                                           None, _lib.raw_stream(torch, self._dev_index))
+        _lib.check(rc)
+        primitive_indices._smesh_counted = (id(self), self._epoch_gen, epoch)
+        return True
+
     def _rider_candidate(self, count_next):
         """The next view's index image if its count stage can ride in this view's scatter launch: a contiguous int32 /
         uint32 device tensor of fewer than 2^24 pixels (the histogram does not depend on the pixel order)."""

@@ -14,7 +14,8 @@ from . import _lib
 
 
 class ViewPipeline:
-    def __init__(self, renderer, aggregator, fused_count=False, count_ahead=False, write_depth=False, group=1):
+    def __init__(self, renderer, aggregator, fused_count=False, count_ahead=False, write_depth=False, group=1,
+                 count_stream=False):
         torch = _lib.require_cuda()
         self.fused_count = bool(fused_count)
         # count_ahead: the count stage of view v+1 rides in the scatter launch of view v (MeshAggregator.add(count_next=)).
@@ -24,12 +25,16 @@ class ViewPipeline:
         # write_depth: materialise the depth image of every view although the pipeline has no use for it (bench.py does,
         # so that a timed view is exactly one reference-style render() + add())
         self.write_depth = bool(write_depth)
+        # count_stream: the count stage of every view on a THIRD stream (MeshAggregator.precount), between its render and
+        # its scatter
+        self.count_stream = bool(count_stream)
         # group: views per add_batch call (1 = one add per view); needs predictions that form a regular batch in memory
         self.group = max(1, int(group))
         self._torch = torch
         self.renderer, self.aggregator = renderer, aggregator
         with torch.cuda.device(renderer.device):
             self._render_stream = torch.cuda.Stream()
+            self._count_stream = torch.cuda.Stream() if self.count_stream else None
 
     def run(self, cameras, predictions, weights=None, keep_indices=False):
         """cameras: sequence of data.Camera; predictions: sequence (or batched tensor) of (W, H, C) float32 arrays, one per
@@ -57,6 +62,16 @@ class ViewPipeline:
                                                   depth=self.write_depth)
                     ev = torch.cuda.Event()
                     ev.record(rs)
+                if self._count_stream is not None and not fused:
+                    cs = self._count_stream
+                    cs.wait_event(ev)
+                    if v >= 2:
+                        cs.wait_event(added[v - 2])  # two counter arrays: view v counts into the one view v - 2 used
+                    with torch.cuda.stream(cs):
+                        self.aggregator.precount(idx)
+                        idx.record_stream(cs)
+                        ev = torch.cuda.Event()
+                        ev.record(cs)
                 nxt = (idx, ev)
             if pending is not None:
                 idx_prev, ev_prev = pending
@@ -77,6 +92,8 @@ class ViewPipeline:
                     kept.append(idx_prev)
             pending = nxt
         rs.wait_stream(main)  # the renderer's workspace / outputs are not reused before the last add has been enqueued
+        if self._count_stream is not None:
+            main.wait_stream(self._count_stream)
         return kept if keep_indices else None
 
     @staticmethod

@@ -651,3 +651,25 @@ def test_render_into_buffer_and_without_depth(sm):
         renderer.render(cams[0], out_indices=buf[0].t())
     with pytest.raises(ValueError):
         renderer.render(cams[0], out_indices=torch.zeros((320, 200), dtype=torch.int64, device="cuda"))
+
+
+def test_pipeline_count_stream_matches_sequential(sm):
+    """ViewPipeline(count_stream=True): the count stage of every view on a third stream, over an epoch wrap."""
+    import torch
+    from semantic_meshes import synthetic
+    from semantic_meshes.pipeline import ViewPipeline
+    W, H, C = 160, 120, 19
+    mesh = synthetic.mesh("terrain", 6000, seed=2)
+    renderer = sm.render.triangles(mesh)
+    P = renderer.getPrimitivesNum()
+    base = synthetic.terrain_cameras(7, W, H, 6000, tris_per_view=1500, seed=8)
+    preds7 = torch.stack([synthetic.predictions_torch(W, H, C, seed=v, device="cuda") for v in range(7)])
+    seq = sm.fusion.MeshAggregator(P, C)
+    for v, cam in enumerate(base):
+        idx, _ = renderer.render(cam)
+        seq.add(idx, preds7[v])
+    n = 7 * 45   # 315 views: the 8-bit epoch wraps inside the run
+    ovl = sm.fusion.MeshAggregator(P, C)
+    ViewPipeline(renderer, ovl, count_stream=True).run([base[v % 7] for v in range(n)], [preds7[v % 7] for v in range(n)])
+    torch.cuda.synchronize()
+    torch.testing.assert_close(ovl.state(), 45 * seq.state(), rtol=2e-5, atol=1e-6)
