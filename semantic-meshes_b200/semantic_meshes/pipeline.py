@@ -26,7 +26,8 @@ class ViewPipeline:
         # so that a timed view is exactly one reference-style render() + add())
         self.write_depth = bool(write_depth)
         # count_stream: the count stage of every view on a THIRD stream (MeshAggregator.precount), between its render and
-        # its scatter
+        # its scatter. Off by default: measured 12.3 - 12.4 k against 12.6 k views/s at config 3 (the step is bound by the
+        # SMs' total work, not by the length of either stream)
         self.count_stream = bool(count_stream)
         # group: views per add_batch call (1 = one add per view); needs predictions that form a regular batch in memory
         self.group = max(1, int(group))
