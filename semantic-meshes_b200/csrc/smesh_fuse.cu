@@ -1484,7 +1484,7 @@ static bool ring_config(int C, RingConfig& cfg)
 {
   // consumer warps x stages; one stage = consumer_warps * 32 pixels * C floats (19.5 KB at C = 19)
   if (C <= 24) { cfg = {8, 3}; }
-  else if (C <= 48) { cfg = {4, 4}; }
+  else if (C <= 48) { cfg = {4, 2}; } // cfg2 (C = 40): 2 stages 18.2 us, 3 stages 18.8, 4 stages 20.1 (more CTAs per SM win)
   else if (C <= 96) { cfg = {4, 3}; }
   else if (C <= 192) { cfg = {4, 2}; }
   else if (C <= 400) { cfg = {2, 2}; }
