@@ -172,13 +172,11 @@ __global__ void __launch_bounds__(256) count_runs_kernel(const IdT* __restrict__
 // Grid-wide flags of the batch launch: a counter in global memory that one lane polls until `target` parties have arrived.
 // (All CTAs of the launch are resident together: the grid is sized from the occupancy query; CTAs that have to wait for
 // another kernel's CTAs to leave an SM arrive late, never not at all.)
-// max_sleep_ns: the pause between two polls doubles from 250 ns up to this (hundreds of warps poll ONE word: without the
-// pauses the polls alone saturate its L2 slice and slow everything that hashes there)
-__device__ __forceinline__ void flag_wait(const uint32_t* flag, uint32_t target, int lane, uint32_t max_sleep_ns)
+__device__ __forceinline__ void flag_wait(const uint32_t* flag, uint32_t target, int lane)
 {
   if (lane == 0)
   {
-    uint32_t v, pause = 250;
+    uint32_t v;
     while (true)
     {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
@@ -186,8 +184,7 @@ __device__ __forceinline__ void flag_wait(const uint32_t* flag, uint32_t target,
       {
         break;
       }
-      __nanosleep(pause);
-      pause = min(pause * 2u, max_sleep_ns);
+      __nanosleep(200);
     }
   }
   __syncwarp();
@@ -205,15 +202,14 @@ __device__ __forceinline__ void flag_arrive(uint32_t* flag, int lane)
 
 // The count stage (flat uint32 ids, tagged counters) as a job of ONE warp of a persistent CTA: the CTA's share of the
 // image in chunks of COUNT_UNROLL x 32 pixels, runs inside a 32-pixel group merged into one pair of reductions.
-template <int UNROLL = COUNT_UNROLL>
 __device__ __forceinline__ void count_job_warp(const uint32_t* __restrict__ ids, int64_t npix, uint32_t P32,
                                                uint32_t* __restrict__ counts, uint32_t tag, int lane)
 {
-  for (int64_t base = (int64_t) blockIdx.x * (32 * UNROLL); base < npix; base += (int64_t) gridDim.x * (32 * UNROLL))
+  for (int64_t base = (int64_t) blockIdx.x * (32 * COUNT_UNROLL); base < npix; base += (int64_t) gridDim.x * (32 * COUNT_UNROLL))
   {
-    uint32_t id[UNROLL];
+    uint32_t id[COUNT_UNROLL];
 #pragma unroll
-    for (int k = 0; k < UNROLL; k++)
+    for (int k = 0; k < COUNT_UNROLL; k++)
     {
       const int64_t i = base + k * 32 + lane;
       id[k] = i < npix ? __ldg(ids + i) : INVALID_ID;
@@ -223,7 +219,7 @@ __device__ __forceinline__ void count_job_warp(const uint32_t* __restrict__ ids,
       }
     }
 #pragma unroll
-    for (int k = 0; k < UNROLL; k++)
+    for (int k = 0; k < COUNT_UNROLL; k++)
     {
       const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, id[k], 1);
       const bool head = (lane == 0) || (prev != id[k]);
@@ -830,9 +826,9 @@ __global__ void __maxnreg__(88) scatter_pair_kernel(ScatterArgs a) // (launched 
       {
         if (v >= 2)
         {
-          flag_wait(a.sync + a.batch + (v - 2), consumers, lane, 4000); // view v-2 used this counter array: everybody out?
+          flag_wait(a.sync + a.batch + (v - 2), consumers, lane); // view v-2 used this counter array: everybody out?
         }
-        count_job_warp<8>(a.ids + (size_t) v * a.ids_stride, a.npix, (uint32_t) a.P,
+        count_job_warp(a.ids + (size_t) v * a.ids_stride, a.npix, (uint32_t) a.P,
                        a.counts2 + (size_t) ((a.epoch0 + (uint32_t) v) & 1u) * (size_t) a.P, (a.epoch0 + (uint32_t) v) << COUNT_BITS,
                        lane);
         flag_arrive(a.sync + v, lane);
@@ -904,7 +900,7 @@ __global__ void __maxnreg__(88) scatter_pair_kernel(ScatterArgs a) // (launched 
         const uint32_t vb = view_of(t);
         if (vb > counted_view)
         {
-          flag_wait(a.sync + vb, gridDim.x, lane, 1000); // every CTA's count warp has finished view vb (they go in order)
+          flag_wait(a.sync + vb, gridDim.x, lane); // every CTA's count warp has finished view vb (they go in order)
           counted_view = vb;
         }
       }
