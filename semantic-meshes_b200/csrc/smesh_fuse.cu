@@ -169,37 +169,6 @@ __global__ void __launch_bounds__(256) count_runs_kernel(const IdT* __restrict__
   }
 }
 
-// Grid-wide flags of the batch launch: a counter in global memory that one lane polls until `target` parties have arrived.
-// (All CTAs of the launch are resident together: the grid is sized from the occupancy query; CTAs that have to wait for
-// another kernel's CTAs to leave an SM arrive late, never not at all.)
-__device__ __forceinline__ void flag_wait(const uint32_t* flag, uint32_t target, int lane)
-{
-  if (lane == 0)
-  {
-    uint32_t v;
-    while (true)
-    {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-      if (v >= target)
-      {
-        break;
-      }
-      __nanosleep(200);
-    }
-  }
-  __syncwarp();
-}
-
-__device__ __forceinline__ void flag_arrive(uint32_t* flag, int lane)
-{
-  __threadfence(); // this lane's reductions / loads before the arrival
-  __syncwarp();
-  if (lane == 0)
-  {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
-  }
-}
-
 // The count stage (flat uint32 ids, tagged counters) as a job of ONE warp of a persistent CTA: the CTA's share of the
 // image in chunks of COUNT_UNROLL x 32 pixels, runs inside a 32-pixel group merged into one pair of reductions.
 __device__ __forceinline__ void count_job_warp(const uint32_t* __restrict__ ids, int64_t npix, uint32_t P32,
@@ -283,15 +252,6 @@ struct ScatterArgs
   uint32_t* next_counts;      // [P] the OTHER counter array
   int64_t next_npix;
   uint32_t next_tag;          // its epoch << COUNT_BITS (tagged counters only)
-  // Batch launch of scatter_pair_kernel<..., MULTI = true> (smesh_fuse_add_batch): `batch` equally shaped views in ONE
-  // persistent launch. View b lies `*_stride` elements after view b-1, has epoch epoch0 + b and the counter array
-  // counts2 + ((epoch0 + b) & 1) * P. ntiles = tiles per view. sync = 2 * batch zeroed words: [b] = CTAs whose count warp
-  // has finished view b, [batch + b] = consumer warps that have finished view b.
-  int batch;
-  int64_t probs_stride, ids_stride, weights_stride;
-  uint32_t* counts2;
-  uint32_t epoch0;
-  uint32_t* sync;
 
   float iew;
 };
@@ -675,8 +635,8 @@ __global__ void __launch_bounds__(RIDER ? 320 : 288, RIDER ? 3 : 0) scatter_kern
 // finished chain of its right neighbour to T. Run heads (S or T) issue the 128-bit reductions.
 // ---------------------------------------------------------------------------------------------------------------------
 
-// (A 64-register build for more co-resident rasterizer CTAs was measured in round 2: 94 us per view against 36 - its
-// spills sit in the inner loop; profiles/r02e_coresidency_sweep.txt. Removed.)
+// LEAN: compiled for 8 CTAs of <= 3 consumer warps per SM (64 registers instead of 84, 24 bytes of spills): leaves room
+// for more rasterizer CTAs next to it. Opt-in (SMESH_PAIR_LEAN=1, C = 19), not measured yet.
 // Bank conflicts of the lanes' row loads (lane stride 2 C words). Odd C: 64-bit loads, conflict free. C = 2 (mod 4): the 2 C
 // floats of a lane are whole 16-byte chunks and 128-bit loads are conflict free. C = 0 (mod 4): 128-bit loads, and every
 // group of PADL lanes is shifted by one more 16-byte chunk in shared memory (C = 4, 12, 20: lanes l and l + 4 would meet
@@ -688,13 +648,8 @@ __host__ __device__ constexpr int pair_pad_lanes(int C)
 }
 
 // WIDE: the even-C layout (128-bit loads, padded groups); false = 64-bit loads of the dense tile for every C
-// MULTI: one persistent launch over a BATCH of views (ScatterArgs::batch): the tiles of all views form one sequence, so
-// there is no ramp-up / drain between views; the count warp counts view b+1 while the consumers are in view b (it starts on
-// view b+2 once every consumer warp has left view b, whose counter array it overwrites), and a consumer warp entering view
-// b+1 waits until every CTA's count warp has finished it. The counts are read past the L1 (ld.global.cg): the lines of a
-// counter array may sit there from two views earlier.
-template <int KIND, int CT, bool WIDE = true, bool MULTI = false>
-__global__ void __maxnreg__(88) scatter_pair_kernel(ScatterArgs a) // (launched with at most 320 threads)
+template <int KIND, int CT, bool LEAN = false, bool WIDE = true>
+__global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LEAN ? 64 : 88) scatter_pair_kernel(ScatterArgs a)
 {
   static_assert(CT >= 1 && CT <= CH, "pair kernel holds 2 x Cpad values in registers");
   constexpr int C = CT;
@@ -702,15 +657,11 @@ __global__ void __maxnreg__(88) scatter_pair_kernel(ScatterArgs a) // (launched 
   constexpr int NCHUNK = Cpad / 4;
   constexpr int PADL = WIDE ? pair_pad_lanes(CT) : 0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const bool has_count = MULTI || a.next_ids != nullptr;
+  const bool has_count = a.next_ids != nullptr;
   const int NW = (int) (blockDim.x >> 5) - 1 - (has_count ? 1 : 0); // consumer warps (warp 0 produces, the last may count)
   const int tile_px = NW * 64;
   const size_t stage_floats = (size_t) tile_px * C + (PADL > 0 ? (size_t) (NW * 32 / (PADL > 0 ? PADL : 1)) * 4 : 0);
   const int stages = a.stages;
-  // MULTI: tiles are numbered through the whole batch, tile g = view g / ntiles, tile g % ntiles of it (32-bit: a batch
-  // holds at most 255 views of fewer than 2^24 pixels)
-  const int64_t total_tiles = MULTI ? a.ntiles * a.batch : a.ntiles;
-  const uint32_t view_tiles = (uint32_t) a.ntiles;
 
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + stage_floats * stages);
@@ -738,7 +689,7 @@ __global__ void __maxnreg__(88) scatter_pair_kernel(ScatterArgs a) // (launched 
     int s = 0;
     uint32_t use_parity = 1;
     bool first_pass = true;
-    for (int64_t gtile = blockIdx.x; gtile < total_tiles; gtile += gridDim.x)
+    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
     {
       if (!first_pass)
       {
@@ -748,12 +699,10 @@ __global__ void __maxnreg__(88) scatter_pair_kernel(ScatterArgs a) // (launched 
         }
         __syncwarp();
       }
-      const uint32_t vb = MULTI ? (uint32_t) gtile / view_tiles : 0u;
-      const int64_t tile = MULTI ? (int64_t) ((uint32_t) gtile - vb * view_tiles) : gtile;
       const int64_t px0 = tile * tile_px;
       const int px_n = (int) min((int64_t) tile_px, a.npix - px0);
       float* dst = stage_base + stage_floats * s;
-      const float* src = a.probs + (MULTI ? (size_t) vb * a.probs_stride : 0) + (size_t) px0 * C;
+      const float* src = a.probs + (size_t) px0 * C;
       if (lane == 0)
       {
         mbar_arrive_expect_tx(full_bar + s, (uint32_t) ((size_t) px_n * C * 4)); // C % 4 == 0: whole 16-byte chunks
@@ -782,20 +731,18 @@ __global__ void __maxnreg__(88) scatter_pair_kernel(ScatterArgs a) // (launched 
       int s = 0;
       uint32_t use_parity = 1;
       bool first_pass = true;
-      for (int64_t gtile = blockIdx.x; gtile < total_tiles; gtile += gridDim.x)
+      for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
       {
         if (!first_pass)
         {
           mbar_wait(empty_bar + s, use_parity, a.wait_hint);
         }
-        const uint32_t vb = MULTI ? (uint32_t) gtile / view_tiles : 0u;
-        const int64_t tile = MULTI ? (int64_t) ((uint32_t) gtile - vb * view_tiles) : gtile;
         const int64_t px0 = tile * tile_px;
         const int64_t px_n = min((int64_t) tile_px, a.npix - px0);
         const size_t nfloats = (size_t) px_n * C;
         const uint32_t bulk_bytes = (uint32_t) ((nfloats * 4) & ~(size_t) 15);
         float* dst = stage_base + stage_floats * s;
-        const float* src = a.probs + (MULTI ? (size_t) vb * a.probs_stride : 0) + (size_t) px0 * C;
+        const float* src = a.probs + (size_t) px0 * C;
         for (size_t k = bulk_bytes / 4; k < nfloats; k++)
         {
           dst[k] = src[k];
@@ -818,23 +765,6 @@ __global__ void __maxnreg__(88) scatter_pair_kernel(ScatterArgs a) // (launched 
 
   if (warp == NW + 1)
   {
-    if constexpr (MULTI)
-    {
-      // ===== the count stages of views 1 ... batch-1 (view 0 was counted before the launch) =====
-      const uint32_t consumers = gridDim.x * (uint32_t) NW;
-      for (int v = 1; v < a.batch; v++)
-      {
-        if (v >= 2)
-        {
-          flag_wait(a.sync + a.batch + (v - 2), consumers, lane); // view v-2 used this counter array: everybody out?
-        }
-        count_job_warp(a.ids + (size_t) v * a.ids_stride, a.npix, (uint32_t) a.P,
-                       a.counts2 + (size_t) ((a.epoch0 + (uint32_t) v) & 1u) * (size_t) a.P, (a.epoch0 + (uint32_t) v) << COUNT_BITS,
-                       lane);
-        flag_arrive(a.sync + v, lane);
-      }
-      return;
-    }
     // ===== the next view's count stage (smesh_fuse_add_batch): hidden under this view's scatter =====
     count_job_warp(a.next_ids, a.next_npix, (uint32_t) a.P, a.next_counts, a.next_tag, lane);
     return;
@@ -847,82 +777,44 @@ __global__ void __maxnreg__(88) scatter_pair_kernel(ScatterArgs a) // (launched 
   const bool has_weights = a.weights != nullptr;
 
   // side inputs (L2 gathers) are fetched two tiles ahead (ids, weights) / one tile ahead (counts, which need the ids)
-  // (MULTI: t is a tile number through the whole batch; the pointers of its view)
-  auto view_of = [&](int64_t t) -> uint32_t { return MULTI ? (uint32_t) t / view_tiles : 0u; };
   auto load_ids = [&](int64_t t) -> uint2 {
+    const int64_t i = t * tile_px + lane_px;
     uint2 r = make_uint2(INVALID_ID, INVALID_ID);
-    if (t >= total_tiles)
-    {
-      return r;
-    }
-    const uint32_t vb = view_of(t);
-    const uint32_t* ids = a.ids + (MULTI ? (size_t) vb * a.ids_stride : 0);
-    const int64_t i = (MULTI ? (int64_t) ((uint32_t) t - vb * view_tiles) : t) * tile_px + lane_px;
     if (i + 1 < a.npix)
     {
-      r = __ldg(reinterpret_cast<const uint2*>(ids + i)); // i is even and the id image is 8-byte aligned (checked on host)
+      r = __ldg(reinterpret_cast<const uint2*>(a.ids + i)); // i is even and the id image is 8-byte aligned (checked on host)
     }
     else if (i < a.npix)
     {
-      r.x = __ldg(ids + i);
+      r.x = __ldg(a.ids + i);
     }
     return r;
   };
   auto load_wts = [&](int64_t t) -> float2 {
+    const int64_t i = t * tile_px + lane_px;
     float2 r = make_float2(1.0f, 1.0f);
-    if (has_weights && t < total_tiles)
+    if (has_weights)
     {
-      const uint32_t vb = view_of(t);
-      const float* wts = a.weights + (MULTI ? (size_t) vb * a.weights_stride : 0);
-      const int64_t i = (MULTI ? (int64_t) ((uint32_t) t - vb * view_tiles) : t) * tile_px + lane_px;
-      if (i < a.npix) r.x = __ldg(wts + i);
-      if (i + 1 < a.npix) r.y = __ldg(wts + i + 1);
+      if (i < a.npix) r.x = __ldg(a.weights + i);
+      if (i + 1 < a.npix) r.y = __ldg(a.weights + i + 1);
     }
     return r;
   };
-  // the per-face pixel counts of view vb (MULTI: its own counter array, read past the L1)
-  auto load_n = [&](uint32_t pid, uint32_t vb) -> uint32_t {
-    if constexpr (MULTI)
-    {
-      return pid < P32 ? __ldcg(a.counts2 + (size_t) ((a.epoch0 + vb) & 1u) * (size_t) a.P + pid) : 1u;
-    }
-    else
-    {
-      return pid < P32 ? __ldg(a.counts + pid) : 1u;
-    }
-  };
-  uint32_t counted_view = 0; // MULTI: the counts of all views up to this one are known to be complete (view 0: before the launch)
-  auto ensure_counted = [&](int64_t t) {
-    if constexpr (MULTI)
-    {
-      if (t < total_tiles)
-      {
-        const uint32_t vb = view_of(t);
-        if (vb > counted_view)
-        {
-          flag_wait(a.sync + vb, gridDim.x, lane); // every CTA's count warp has finished view vb (they go in order)
-          counted_view = vb;
-        }
-      }
-    }
-  };
+  auto load_n = [&](uint32_t pid) -> uint32_t { return pid < P32 ? __ldg(a.counts + pid) : 1u; };
 
   int64_t tile = blockIdx.x;
   uint2 id = load_ids(tile), id1 = load_ids(tile + tile_stride);
   float2 wt = load_wts(tile), wt1 = load_wts(tile + tile_stride);
-  ensure_counted(tile);
-  uint2 n = make_uint2(load_n(id.x, view_of(tile)), load_n(id.y, view_of(tile)));
+  uint2 n = make_uint2(load_n(id.x), load_n(id.y));
 
   int s = 0;
   uint32_t parity = 0;
   const float* stage_ptr = stage_base + (size_t) lane_px * C + (PADL > 0 ? (size_t) ((cw * 32 + lane) / (PADL > 0 ? PADL : 1)) * 4 : 0);
-  for (; tile < total_tiles; tile += tile_stride)
+  for (; tile < a.ntiles; tile += tile_stride)
   {
     const uint2 id2 = load_ids(tile + 2 * tile_stride);
     const float2 wt2 = load_wts(tile + 2 * tile_stride);
-    ensure_counted(tile + tile_stride);
-    const uint32_t vb1 = view_of(min(tile + tile_stride, total_tiles - 1));
-    const uint2 n1 = make_uint2(load_n(id1.x, vb1), load_n(id1.y, vb1));
+    const uint2 n1 = make_uint2(load_n(id1.x), load_n(id1.y));
 
     mbar_wait(full_bar + s, parity, a.wait_hint);
     // ---- both pixels' class vectors: 2C contiguous floats, C 64-bit loads (even C: C / 2 128-bit loads) ----
@@ -1093,17 +985,6 @@ __global__ void __maxnreg__(88) scatter_pair_kernel(ScatterArgs a) // (launched 
     {
       s = 0;
       parity ^= 1u;
-    }
-    if constexpr (MULTI)
-    {
-      // this warp's last tile of view vb: it no longer reads that view's counter array. (The host launches this build only
-      // when a view has at least gridDim.x tiles: every warp has tiles in every view and its next tile lies in the same
-      // view or in the next one.)
-      const uint32_t vb = view_of(tile);
-      if (tile + tile_stride >= total_tiles || view_of(tile + tile_stride) != vb)
-      {
-        flag_arrive(a.sync + a.batch + vb, lane);
-      }
     }
     id = id1; id1 = id2;
     wt = wt1; wt1 = wt2;
@@ -1708,22 +1589,30 @@ constexpr bool pair_wide_default(int C)
   return C == 20 || C == 12;
 }
 
-template <int KIND, int CT>
+template <int KIND, int CT, bool LEAN = false>
 static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
 {
   ScatterArgs args = args_in;
   const PairConfig cfg = pair_config(CT);
+  if (CT == 19 && !LEAN && cfg.consumer_warps <= 3)
+  {
+    static const bool lean = getenv("SMESH_PAIR_LEAN") != nullptr && atoi(getenv("SMESH_PAIR_LEAN")) != 0;
+    if (lean)
+    {
+      return launch_scatter_pair<KIND, CT == 19 ? 19 : 2, CT == 19>(args_in, stream);
+    }
+  }
   // C = 12, 20: the padded layout (see scatter_pair_kernel); SMESH_PAIR_WIDE=0 switches it off (tuning)
   static const int env_wide = getenv("SMESH_PAIR_WIDE") ? atoi(getenv("SMESH_PAIR_WIDE")) : -1;
-  const bool wide = pair_wide_default(CT) && env_wide != 0;
+  const bool wide = pair_wide_default(CT) && !LEAN && env_wide != 0;
   const int padl = wide ? pair_pad_lanes(CT) : 0;
   const size_t smem = (size_t) cfg.stages * (cfg.consumer_warps * 64 * CT * 4 + (padl > 0 ? (cfg.consumer_warps * 32 / padl) * 16 : 0)) +
                       (size_t) cfg.stages * 16 +
                       (size_t) cfg.consumer_warps * (64 * ((CT + 3) & ~3) + 64) * 4; // flush rows + their face ids
-  void (*kernel)(ScatterArgs) = scatter_pair_kernel<KIND, CT, false>;
-  if constexpr (pair_wide_default(CT))
+  void (*kernel)(ScatterArgs) = scatter_pair_kernel<KIND, CT, LEAN, false>;
+  if constexpr (pair_wide_default(CT) && !LEAN)
   {
-    if (wide) kernel = scatter_pair_kernel<KIND, CT, true>;
+    if (wide) kernel = scatter_pair_kernel<KIND, CT, LEAN, true>;
   }
   const int threads = (cfg.consumer_warps + 1 + (args.next_ids != nullptr ? 1 : 0)) * 32;
   int blocks_per_sm = 0;
@@ -1751,55 +1640,6 @@ static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
 
 // Can the scatter launch of these arguments carry the next view's count stage? (the two ring kernels can)
 static bool scatter_takes_count_job(int kind, const ScatterArgs& args);
-
-// One persistent launch over a batch of views (scatter_pair_kernel<..., MULTI = true>). -> SMESH_ERR_UNSUPPORTED (and no
-// launch, no error text) when this batch has to go view by view: a view with fewer tiles than the grid has CTAs.
-template <int KIND, int CT>
-static int launch_scatter_pair_batch(const ScatterArgs& args_in, cudaStream_t stream)
-{
-  ScatterArgs args = args_in;
-  const PairConfig cfg = pair_config(CT);
-  const bool wide = pair_wide_default(CT);
-  const int padl = wide ? pair_pad_lanes(CT) : 0;
-  const size_t smem = (size_t) cfg.stages * (cfg.consumer_warps * 64 * CT * 4 + (padl > 0 ? (cfg.consumer_warps * 32 / padl) * 16 : 0)) +
-                      (size_t) cfg.stages * 16 + (size_t) cfg.consumer_warps * (64 * ((CT + 3) & ~3) + 64) * 4;
-  void (*kernel)(ScatterArgs) = scatter_pair_kernel<KIND, CT, pair_wide_default(CT), true>;
-  const int threads = (cfg.consumer_warps + 2) * 32;
-  int blocks_per_sm = 0;
-  const int cfg_rc = kernel_blocks_per_sm(reinterpret_cast<const void*>(kernel), threads, smem, &blocks_per_sm);
-  if (cfg_rc != SMESH_OK)
-  {
-    return cfg_rc;
-  }
-  const int tile_px = cfg.consumer_warps * 64;
-  args.ntiles = (args.npix + tile_px - 1) / tile_px;
-  args.stages = cfg.stages;
-  const int64_t blocks = (int64_t) num_sms() * std::min(blocks_per_sm, 4);
-  if (blocks_per_sm < 1 || args.ntiles < blocks || args.ntiles * args.batch >= 0x7FFFFFFFll)
-  {
-    return SMESH_ERR_UNSUPPORTED;
-  }
-  kernel<<<(unsigned) blocks, threads, smem, stream>>>(args);
-  SMESH_LAUNCH_CHECK("scatter_pair_kernel (batch)");
-  return SMESH_OK;
-}
-
-template <int KIND>
-static int launch_scatter_batch(const ScatterArgs& args, cudaStream_t stream)
-{
-  if ((reinterpret_cast<uintptr_t>(args.probs) & 15) != 0 || (reinterpret_cast<uintptr_t>(args.ids) & 7) != 0 ||
-      (args.probs_stride * 4) % 16 != 0 || (args.ids_stride * 4) % 8 != 0)
-  {
-    return SMESH_ERR_UNSUPPORTED;
-  }
-  switch (args.C)
-  {
-#define SMESH_PAIR_BATCH_CASE(c) case c: return launch_scatter_pair_batch<KIND, c>(args, stream);
-    SMESH_PAIR_BATCH_CASE(19) SMESH_PAIR_BATCH_CASE(20) SMESH_PAIR_BATCH_CASE(13) SMESH_PAIR_BATCH_CASE(3)
-#undef SMESH_PAIR_BATCH_CASE
-    default: return SMESH_ERR_UNSUPPORTED;
-  }
-}
 
 template <int KIND>
 static int launch_scatter(const ScatterArgs& args, cudaStream_t stream)
@@ -1918,11 +1758,6 @@ static ScatterArgs make_scatter_args(const uint32_t* ids32, const float* probs, 
   args.next_counts = nullptr;
   args.next_npix = 0;
   args.next_tag = 0;
-  args.batch = 1;
-  args.probs_stride = args.ids_stride = args.weights_stride = 0;
-  args.counts2 = nullptr;
-  args.epoch0 = 0;
-  args.sync = nullptr;
   return args;
 }
 
@@ -2264,46 +2099,6 @@ extern "C" int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id
   // ScatterArgs): it needs tagged counters (two arrays in flight), ids that are consumed in place (no ids32 scratch) and a
   // scatter kernel with a spare warp. Otherwise the stages simply alternate.
   bool counted = false; // view b's counts are already in flight
-  static const bool no_batch_kernel = getenv("SMESH_NO_BATCH_KERNEL") != nullptr; // profiling only
-  if (B >= 2 && count_epoch0 != 0 && kind != SMESH_KIND_SUMMAX && !no_overlap && !no_batch_kernel)
-  {
-    // ONE persistent launch for the whole batch where the two-pixels-per-lane kernel applies (narrow class vectors, ids
-    // consumed in place, views of at least one tile per CTA): no ramp-up / drain between the views
-    ViewStages v0;
-    rc = view(0, v0);
-    if (rc != SMESH_OK)
-    {
-      return rc;
-    }
-    if (v0.zero_copy && 2 * B <= n_outer * n_inner)
-    {
-      rc = v0.count(counts_of(0), epoch_of(0), stream);
-      if (rc != SMESH_OK)
-      {
-        return rc;
-      }
-      counted = true;
-      ScatterArgs args = make_scatter_args(v0.flat_ids(), v0.probs, v0.weights, counts_of(0), acc, v0.npix(), C, P, iew, count_epoch0);
-      args.batch = (int) B;
-      args.probs_stride = probs_stride_view;
-      args.ids_stride = ids_stride_view;
-      args.weights_stride = w_stride_view;
-      args.counts2 = counts2;
-      args.epoch0 = count_epoch0;
-      args.sync = ids32; // (the flat-id scratch is unused when the ids are consumed in place)
-      SMESH_CUDA_CHECK(cudaMemsetAsync(ids32, 0, sizeof(uint32_t) * 2 * (size_t) B, stream));
-      rc = kind == SMESH_KIND_SUM ? launch_scatter_batch<SMESH_KIND_SUM>(args, stream) : launch_scatter_batch<SMESH_KIND_MUL>(args, stream);
-      if (rc == SMESH_OK)
-      {
-        return SMESH_OK;
-      }
-      if (rc != SMESH_ERR_UNSUPPORTED)
-      {
-        return rc;
-      }
-      // not a shape for the batch kernel: view by view below, view 0 is counted already
-    }
-  }
   for (int64_t b = 0; b < B; b++)
   {
     ViewStages v, vn;

@@ -830,41 +830,3 @@ def test_ring_kernel_padded_layouts(sm, kind, C):
         ref.add(i, p)
     assert_acc_close(kind, agg.state().cpu().numpy(), ref.acc)
     assert_get_close(kind, agg.get(), ref.get())
-
-
-@pytest.mark.parametrize("kind,C", [("sum", 19), ("mul", 19), ("sum", 20), ("sum", 13), ("sum", 3)])
-def test_add_batch_single_launch(sm, kind, C):
-    """Batches of views with at least one tile per CTA (>= 114 k pixels) and C in {3, 13, 19, 20} go through ONE persistent
-    scatter launch (the count warps run a view ahead, grid-wide flags order them against the consumers): same result as
-    the loop of add() calls, with weights, for 2 ... 7 views, repeated (the flags live in a scratch buffer that is reused),
-    and captured into a CUDA graph."""
-    import torch
-    rng = np.random.default_rng(C * 5 + len(kind))
-    W, H, P = 400, 301, 700
-    for B in (2, 3, 7):
-        views = [make_view(rng, W, H, C, P, block=1 + (b % 5)) for b in range(B)]
-        ids = torch.from_numpy(np.stack([v[0] for v in views]).view(np.int32)).cuda()
-        probs = torch.from_numpy(np.stack([v[1] for v in views])).cuda()
-        wts = torch.from_numpy((rng.random((B, W, H)) * 2).astype(np.float32)).cuda() if B == 3 else None
-        ref = oracle.Aggregator(P, C, kind)
-        for b, (i, p) in enumerate(views):
-            ref.add(i, p, None if wts is None else wts[b].cpu().numpy())
-        a = sm.fusion.MeshAggregator(P, C, kind)
-        a.add_batch(ids, probs, wts)
-        assert_acc_close(kind, a.state().cpu().numpy(), ref.acc)
-        a.add_batch(ids, probs, wts)
-        exp2 = np.where(np.isinf(ref.acc), ref.acc, 2 * ref.acc)
-        assert_acc_close(kind, a.state().cpu().numpy(), exp2, rtol=2e-5)
-    g_agg = sm.fusion.MeshAggregator(P, C, kind)
-    g_agg.restart_epochs()
-    g_agg.add_batch(ids, probs, wts)
-    torch.cuda.synchronize()
-    g_agg.reset()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        g_agg.restart_epochs()
-        g_agg.add_batch(ids, probs, wts)
-    graph.replay()
-    graph.replay()
-    torch.cuda.synchronize()
-    assert_acc_close(kind, g_agg.state().cpu().numpy(), exp2, rtol=2e-5)
