@@ -635,8 +635,8 @@ __global__ void __launch_bounds__(RIDER ? 320 : 288, RIDER ? 3 : 0) scatter_kern
 // finished chain of its right neighbour to T. Run heads (S or T) issue the 128-bit reductions.
 // ---------------------------------------------------------------------------------------------------------------------
 
-// LEAN: compiled for 8 CTAs of <= 3 consumer warps per SM (64 registers instead of 84, 24 bytes of spills): leaves room
-// for more rasterizer CTAs next to it. Opt-in (SMESH_PAIR_LEAN=1, C = 19), not measured yet.
+// (A 64-register build for more co-resident rasterizer CTAs was measured in round 2: 94 us per view against 36 - its
+// spills sit in the inner loop; profiles/r02e_coresidency_sweep.txt. Removed.)
 // Bank conflicts of the lanes' row loads (lane stride 2 C words). Odd C: 64-bit loads, conflict free. C = 2 (mod 4): the 2 C
 // floats of a lane are whole 16-byte chunks and 128-bit loads are conflict free. C = 0 (mod 4): 128-bit loads, and every
 // group of PADL lanes is shifted by one more 16-byte chunk in shared memory (C = 4, 12, 20: lanes l and l + 4 would meet
@@ -648,8 +648,8 @@ __host__ __device__ constexpr int pair_pad_lanes(int C)
 }
 
 // WIDE: the even-C layout (128-bit loads, padded groups); false = 64-bit loads of the dense tile for every C
-template <int KIND, int CT, bool LEAN = false, bool WIDE = true>
-__global__ void __launch_bounds__(LEAN ? 160 : 320, LEAN ? 8 : 0) __maxnreg__(LEAN ? 64 : 88) scatter_pair_kernel(ScatterArgs a)
+template <int KIND, int CT, bool WIDE = true>
+__global__ void __maxnreg__(88) scatter_pair_kernel(ScatterArgs a) // (launched with at most 320 threads)
 {
   static_assert(CT >= 1 && CT <= CH, "pair kernel holds 2 x Cpad values in registers");
   constexpr int C = CT;
@@ -1589,30 +1589,22 @@ constexpr bool pair_wide_default(int C)
   return C == 20 || C == 12;
 }
 
-template <int KIND, int CT, bool LEAN = false>
+template <int KIND, int CT>
 static int launch_scatter_pair(const ScatterArgs& args_in, cudaStream_t stream)
 {
   ScatterArgs args = args_in;
   const PairConfig cfg = pair_config(CT);
-  if (CT == 19 && !LEAN && cfg.consumer_warps <= 3)
-  {
-    static const bool lean = getenv("SMESH_PAIR_LEAN") != nullptr && atoi(getenv("SMESH_PAIR_LEAN")) != 0;
-    if (lean)
-    {
-      return launch_scatter_pair<KIND, CT == 19 ? 19 : 2, CT == 19>(args_in, stream);
-    }
-  }
   // C = 12, 20: the padded layout (see scatter_pair_kernel); SMESH_PAIR_WIDE=0 switches it off (tuning)
   static const int env_wide = getenv("SMESH_PAIR_WIDE") ? atoi(getenv("SMESH_PAIR_WIDE")) : -1;
-  const bool wide = pair_wide_default(CT) && !LEAN && env_wide != 0;
+  const bool wide = pair_wide_default(CT) && env_wide != 0;
   const int padl = wide ? pair_pad_lanes(CT) : 0;
   const size_t smem = (size_t) cfg.stages * (cfg.consumer_warps * 64 * CT * 4 + (padl > 0 ? (cfg.consumer_warps * 32 / padl) * 16 : 0)) +
                       (size_t) cfg.stages * 16 +
                       (size_t) cfg.consumer_warps * (64 * ((CT + 3) & ~3) + 64) * 4; // flush rows + their face ids
-  void (*kernel)(ScatterArgs) = scatter_pair_kernel<KIND, CT, LEAN, false>;
-  if constexpr (pair_wide_default(CT) && !LEAN)
+  void (*kernel)(ScatterArgs) = scatter_pair_kernel<KIND, CT, false>;
+  if constexpr (pair_wide_default(CT))
   {
-    if (wide) kernel = scatter_pair_kernel<KIND, CT, LEAN, true>;
+    if (wide) kernel = scatter_pair_kernel<KIND, CT, true>;
   }
   const int threads = (cfg.consumer_warps + 1 + (args.next_ids != nullptr ? 1 : 0)) * 32;
   int blocks_per_sm = 0;
