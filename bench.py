@@ -612,7 +612,7 @@ def run_ours(args, cfg):
                    "timed_region_ms": elapsed_ms},
         "mpixel_face_scatters_per_s": value * float(np.mean(scene.accepted)) / 1e6,
         "stages": stages,
-        "roofline": {"bound": "hbm", "kernel": "MeshAggregator.add = smesh::fuse::count_kernel + scatter kernel "
+        "roofline": {"bound": "hbm", "kernel": "MeshAggregator.add = smesh::fuse::count_runs_kernel + scatter kernel "
                                                "(scatter_pair_kernel at C <= 20, scatter_rows_kernel at wide C)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src,

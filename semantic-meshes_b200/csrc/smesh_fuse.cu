@@ -3,7 +3,7 @@
 //
 // The reference copies the view to the host, builds a serial std::map histogram and then does a mutex-guarded vector add
 // per pixel under OpenMP. Here one view is three launches on the caller's stream:
-//   1. count_kernel   - per-face pixel count of this view (Mesh.h:90-93), runs of equal ids inside a warp merged into
+//   1. count_runs_kernel - per-face pixel count of this view (Mesh.h:90-93), runs of equal ids inside a warp merged into
 //                       one atomicAdd; also writes the flat-order uint32 copy of the ids when the input is strided or
 //                       not 32-bit
 //   2. scatter_kernel - THE hot kernel, HBM-bound: the (n_pix, C) probability image is streamed exactly once through a
@@ -16,6 +16,10 @@
 //                       (C = 2 ... 20: scatter_pair_kernel, two pixels per lane; wide C: scatter_rows_kernel, lanes across the
 //                       classes of a pixel, rows read straight from global memory)
 //   3. clear_kernel   - only in the untagged-counter mode (images of >= 2^24 pixels): zero the touched counters again
+// Inside a batch (smesh_fuse_add_batch) and for callers that hold the next index image early
+// (smesh_fuse_scatter_count_next) stage 1 of the NEXT view rides in stage 2 of this one: one more warp per CTA of the
+// ring kernels (count_job_warp) takes the next view's counts into the other of two counter arrays.
+// get() (get_kernel) stages accumulator rows through shared memory: coalesced in, one thread per row, coalesced out.
 // No tensor cores: this is an irregular gather/scatter, not a contraction.
 #include "smesh_common.cuh"
 
