@@ -518,6 +518,24 @@ def run_ours(args, cfg):
     full = rank == 0 and not args.quick
     stages = stage_timings(args, scene, agg, use_graph, kinds=("sum", "summax", "mul") if full else ("sum",), with_get=full)
     stages["allreduce_ms"] = allreduce_ms
+    if dist is not None:
+        # the cheaper end of a sharded job: reduce-scatter + get() on this rank's rows (against all-reduce + full get())
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev = [torch.cuda.Event(True) for _ in range(3)]
+        agg.reduce_scatter_get()
+        ev[0].record()
+        agg.reduce_scatter_get()
+        ev[1].record()
+        scratch = agg._acc.clone()
+        dist.all_reduce(scratch)
+        agg.get(device=True)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stages["reduce_scatter_get_ms"], stages["allreduce_plus_full_get_ms"] = float(t[0]), float(t[1])
+        del scratch
     if allreduce_cold_ms is not None:
         nbytes = agg._acc.numel() * 4
         stages.update({"allreduce_ms_cold_first_call": allreduce_cold_ms, "allreduce_ms_warm": allreduce_warm_ms,
