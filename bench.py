@@ -523,11 +523,13 @@ def run_ours(args, cfg):
         torch.cuda.synchronize()
         dist.barrier()
         ev = [torch.cuda.Event(True) for _ in range(3)]
+        scratch = agg._acc.clone()
         agg.reduce_scatter_get()
+        agg.get(device=True)
+        torch.cuda.synchronize()
         ev[0].record()
         agg.reduce_scatter_get()
         ev[1].record()
-        scratch = agg._acc.clone()
         dist.all_reduce(scratch)
         agg.get(device=True)
         ev[2].record()
