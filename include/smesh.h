@@ -92,9 +92,9 @@ int smesh_raster_workspace_bytes(int64_t V, int64_t F, int W, int H, size_t* byt
  *   f_host  double[2] focal lengths, c_host double[2] principal point (Camera::intr; the Python Camera rounds its
  *           inputs to float first and then widens, python/semantic_meshes/include/Camera.h:19-54 - the caller does it)
  *   W, H    Camera::resolution (1 <= W, H <= 65536)
- *   workspace  device scratch of smesh_raster_workspace_bytes(V, F, W, H) bytes; ZERO-FILL it once after allocating it
- *           (it caches a per-pixel table keyed by the intrinsics and the cleared depth buffer) and keep it for the next
- *           views of the same mesh; one workspace serves one stream at a time
+ *   workspace  device scratch of smesh_raster_workspace_bytes(V, F, W, H) bytes (ray tables, packed depth buffer, unit
+ *           list, big-triangle queue): every view initialises what it uses, nothing is carried from view to view; keep
+ *           it for the next views of the same mesh and resolution; one workspace serves one stream at a time
  *   idx_out uint32[W][H] (0xFFFFFFFF where nothing is hit), depth_out float32[W][H] (+inf where nothing is hit; may be
  *           NULL when the caller only fuses the view: the depth image is then not written)
  * Results are bit-identical to the reference kernel as compiled by nvcc 12.9 for sm_100a, with the one documented
