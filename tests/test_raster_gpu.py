@@ -344,7 +344,7 @@ def test_fuzz_random_scenes(sm, seed):
 
 
 def test_intrinsics_change_rebuilds_ray_table(sm):
-    """The per-pixel ray normalisation is cached per intrinsics inside the renderer's workspace."""
+    """One renderer, changing intrinsics from view to view (the ray tables of the workspace are rebuilt per view)."""
     from semantic_meshes import synthetic
     from semantic_meshes.data import Camera
     mesh = synthetic.mesh("icosphere")
