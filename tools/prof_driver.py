@@ -1,4 +1,4 @@
-"""Small driver for ncu: a few eager views of one bench config (render + add), nothing else on the GPU."""
+"""Small driver for ncu: a few eager views of one bench config (render + add), then get() - nothing else on the GPU."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "semantic-meshes_b200")]
@@ -20,5 +20,6 @@ for rep in range(2):
     for b in range(views):
         idx, _ = renderer.render(cams[b])
         agg.add(idx, probs[b])
+out = agg.get(device=True)
 torch.cuda.synchronize()
-print("done")
+print("done", float(out.sum()))
