@@ -56,19 +56,43 @@ __device__ __forceinline__ float pixel_weight(float iew, uint32_t n, float wt)
   return __fmul_rn(w, wt);
 }
 
+// log(x) for a NORMAL, positive, finite x (the caller checks): exponent / mantissa split with the mantissa in [2/3, 4/3),
+// log1p(f) = f - f^2/2 + f^3 Q(f) with a degree-7 Q fitted over [-1/3, 1/3]. Maximum error 0.77 ulp on the mantissa part
+// (all 2^23 x 2/3 floats of [2/3, 4/3) checked, tests/golden/fit_log.py), ~1.3 ulp overall: the same class as logf (1 ulp),
+// at 17 instructions without logf's handling of zero, denormals, infinities and NaN.
+__device__ __forceinline__ float log_normal(float x)
+{
+  const int i = __float_as_int(x);
+  const int e = (i - 0x3f2aaaab) & (int) 0xff800000;
+  const float f = __int_as_float(i - e) - 1.0f;
+  const float fe = (float) (e >> 23);
+  float q = -0.12890197336673737f;
+  q = fmaf(q, f, 0.13985218107700348f);
+  q = fmaf(q, f, -0.12184639275074005f);
+  q = fmaf(q, f, 0.14005699753761292f);
+  q = fmaf(q, f, -0.16680456697940826f);
+  q = fmaf(q, f, 0.20010416209697723f);
+  q = fmaf(q, f, -0.24999798834323883f);
+  q = fmaf(q, f, 0.3333321511745453f);
+  const float s = f * f;
+  const float r = fmaf(fmaf(q, f, -0.5f), s, f);
+  return fmaf(fe, 0.693147182f, r);
+}
+
 // mul aggregator input: LogProb(pow(p, w)) as -log (Fusion.cu:83-87, tt/numeric/LogProb.h:66-71); "zero" (isinf of
 // either sign) is the absorbing +inf (LogProb.h:106-118).
 // The reference's powf + logf pair costs ~150 instructions per class. -log(p^w) = -w log p, and as long as q = p^w stays a
-// normal float (|w log p| < 80, p > 0, w > 0) the reference's value is -log(fl(q)) = -w log p within 6e-8 absolute (the
-// rounding of q, which the direct form does not even have) + 2e-7 relative (logf): the direct form is used there. Anything
-// else - underflow of q to the absorbing zero, overflow, p <= 0, NaN, w <= 0 - takes the reference's own sequence.
-// `exact` (SMESH_MUL_EXACT=1, verification) forces that sequence everywhere.
+// normal float (|w log p| < 80, p a normal positive float, w > 0) the reference's value is -log(fl(q)) = -w log p within
+// 6e-8 absolute (the rounding of q, which the direct form does not even have) + 2e-7 relative (the two logarithms): the
+// direct form is used there, with log_normal() above. Anything else - underflow of q to the absorbing zero, overflow,
+// p <= 0 or denormal, NaN, w <= 0 - takes the reference's own sequence. `exact` (SMESH_MUL_EXACT=1, verification) forces
+// that sequence everywhere.
 __device__ __forceinline__ float neg_log_pow(float p, float w, bool exact)
 {
-  if (!exact)
+  if (!exact && __float_as_uint(p) - 0x00800000u < 0x7F000000u && w > 0.0f) // 0x00800000 <= bits < 0x7F800000: normal, positive
   {
-    const float l = __fmul_rn(-w, logf(p));
-    if (p > 0.0f && w > 0.0f && fabsf(l) < 80.0f)
+    const float l = -w * log_normal(p);
+    if (fabsf(l) < 80.0f)
     {
       return l;
     }
