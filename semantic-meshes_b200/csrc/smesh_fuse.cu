@@ -87,16 +87,10 @@ __device__ __forceinline__ float log_normal(float x)
 // direct form is used there, with log_normal() above. Anything else - underflow of q to the absorbing zero, overflow,
 // p <= 0 or denormal, NaN, w <= 0 - takes the reference's own sequence. `exact` (SMESH_MUL_EXACT=1, verification) forces
 // that sequence everywhere.
-__device__ __forceinline__ float neg_log_pow(float p, float w, bool exact)
+// (out of line: inlined at each of the 38 call sites of a tile, powf + logf made the loop body of the mul kernels some
+// 4000 instructions long - more than the instruction caches hold)
+__device__ __noinline__ float neg_log_pow_reference(float p, float w)
 {
-  if (!exact && __float_as_uint(p) - 0x00800000u < 0x7F000000u && w > 0.0f) // 0x00800000 <= bits < 0x7F800000: normal, positive
-  {
-    const float l = -w * log_normal(p);
-    if (fabsf(l) < 80.0f)
-    {
-      return l;
-    }
-  }
   const float q = powf(p, w);
   float l = (q == 0.0f) ? CUDART_INF_F : -logf(q);
   if (isinf(l))
@@ -104,6 +98,29 @@ __device__ __forceinline__ float neg_log_pow(float p, float w, bool exact)
     l = CUDART_INF_F;
   }
   return l;
+}
+
+// the direct form of one element, computed unconditionally; `bad` is raised where it does not apply to the element
+__device__ __forceinline__ float neg_log_pow_direct(float p, float w, bool& bad)
+{
+  const float l = -w * log_normal(p);
+  bad |= !(__float_as_uint(p) - 0x00800000u < 0x7F000000u) || !(fabsf(l) < 80.0f); // 0x00800000 <= bits < 0x7F800000: normal, positive
+  return l;
+}
+
+// one element: the direct form where it applies, else the reference's sequence
+__device__ __forceinline__ float neg_log_pow(float p, float w, bool exact)
+{
+  bool bad = exact || !(w > 0.0f);
+  const float l = neg_log_pow_direct(p, w, bad);
+  return bad ? neg_log_pow_reference(p, w) : l;
+}
+
+// (the per-element choice out of line, for the rare second pass of a class vector that held an element the direct form
+// does not cover: the kernels evaluate a whole vector in the direct form without branches first)
+__device__ __noinline__ float neg_log_pow_checked(float p, float w, bool exact)
+{
+  return neg_log_pow(p, w, exact);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -592,16 +609,38 @@ __global__ void __launch_bounds__(RIDER ? 320 : 288, RIDER ? 3 : 0) scatter_kern
         {
           load_chunk(row + c0, nv, al, v);
         }
-#pragma unroll
-        for (int k = 0; k < CH; k++)
+        if (KIND == SMESH_KIND_SUM)
         {
-          if (KIND == SMESH_KIND_SUM)
+#pragma unroll
+          for (int k = 0; k < CH; k++)
           {
             v[k] = __fmul_rn(v[k], w); // weighted::sum (tt/aggregator/MiscOps.h:83-93): acc += probs * w
           }
-          else
+        }
+        else
+        {
+          // the chunk in the direct form, branch-free; redone element by element if one is outside its domain
+          float l[CH];
+          bool bad = a.mul_exact != 0 || !(w > 0.0f);
+#pragma unroll
+          for (int k = 0; k < CH; k++)
           {
-            v[k] = (k < nv && ok) ? neg_log_pow(v[k], w, a.mul_exact != 0) : 0.0f;
+            bool bad_k = false;
+            l[k] = neg_log_pow_direct(v[k], w, bad_k);
+            bad |= bad_k && k < nv;
+          }
+          if (bad && ok)
+          {
+#pragma unroll
+            for (int k = 0; k < CH; k++)
+            {
+              l[k] = neg_log_pow_checked(v[k], w, a.mul_exact != 0);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < CH; k++)
+          {
+            v[k] = (k < nv && ok) ? l[k] : 0.0f;
           }
         }
         // segmented suffix sum over the run (log2(longest run) shuffle rounds, warp-uniform)
@@ -890,18 +929,43 @@ __global__ void __maxnreg__(88) scatter_pair_kernel(ScatterArgs a) // (launched 
     const bool okB = id.y < P32 && sumB > 0.5f;
     const float wA = pixel_weight(a.iew, n.x & a.count_mask, wt.x);
     const float wB = pixel_weight(a.iew, n.y & a.count_mask, wt.y);
-#pragma unroll
-    for (int k = 0; k < Cpad; k++)
+    if (KIND == SMESH_KIND_SUM)
     {
-      if (KIND == SMESH_KIND_SUM)
+#pragma unroll
+      for (int k = 0; k < Cpad; k++)
       {
         A[k] = __fmul_rn(A[k], wA); // weighted::sum (tt/aggregator/MiscOps.h:83-93): acc += probs * w
         B[k] = __fmul_rn(B[k], wB);
       }
-      else
+    }
+    else
+    {
+      // both vectors in the direct form, branch-free; a vector with an element outside its domain is redone element by
+      // element from the stage (still owned by this warp until the end of the iteration)
+      bool badA = a.mul_exact != 0 || !(wA > 0.0f), badB = a.mul_exact != 0 || !(wB > 0.0f);
+#pragma unroll
+      for (int k = 0; k < C; k++)
       {
-        A[k] = (k < C && okA) ? neg_log_pow(A[k], wA, a.mul_exact != 0) : 0.0f;
-        B[k] = (k < C && okB) ? neg_log_pow(B[k], wB, a.mul_exact != 0) : 0.0f;
+        A[k] = neg_log_pow_direct(A[k], wA, badA);
+        B[k] = neg_log_pow_direct(B[k], wB, badB);
+      }
+      badA = badA && okA;
+      badB = badB && okB;
+      if (badA || badB)
+      {
+        const float* rowf = stage_ptr + stage_floats * s;
+#pragma unroll
+        for (int k = 0; k < C; k++)
+        {
+          if (badA) A[k] = neg_log_pow_checked(rowf[k], wA, a.mul_exact != 0);
+          if (badB) B[k] = neg_log_pow_checked(rowf[C + k], wB, a.mul_exact != 0);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < C; k++)
+      {
+        A[k] = okA ? A[k] : 0.0f;
+        B[k] = okB ? B[k] : 0.0f;
       }
     }
 
@@ -1224,22 +1288,55 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(ScatterArgs a)
             flush();
             cur = idu[u];
           }
-#pragma unroll
-          for (int p = 0; p < NP; p++)
+          if (KIND == SMESH_KIND_SUM)
           {
 #pragma unroll
-            for (int k = 0; k < VW; k++)
+            for (int p = 0; p < NP; p++)
             {
-              if (KIND == SMESH_KIND_SUM)
+#pragma unroll
+              for (int k = 0; k < VW; k++)
               {
                 acc[p][k] = __fadd_rn(acc[p][k], __fmul_rn(v[u][p][k], wu[u])); // acc += probs * w (MiscOps.h:83-93)
               }
-              else
+            }
+          }
+          else
+          {
+            // this lane's elements in the direct form, branch-free; redone one by one if one is outside its domain
+            float l[NP][VW];
+            bool bad = a.mul_exact != 0 || !(wu[u] > 0.0f);
+#pragma unroll
+            for (int p = 0; p < NP; p++)
+            {
+#pragma unroll
+              for (int k = 0; k < VW; k++)
               {
-                const int c = j + p * LG;
-                if (c < K)
+                bool bad_k = false;
+                l[p][k] = neg_log_pow_direct(v[u][p][k], wu[u], bad_k);
+                bad |= bad_k && j + p * LG < K;
+              }
+            }
+            if (bad)
+            {
+#pragma unroll
+              for (int p = 0; p < NP; p++)
+              {
+#pragma unroll
+                for (int k = 0; k < VW; k++)
                 {
-                  acc[p][k] = __fadd_rn(acc[p][k], neg_log_pow(v[u][p][k], wu[u], a.mul_exact != 0));
+                  l[p][k] = neg_log_pow_checked(v[u][p][k], wu[u], a.mul_exact != 0);
+                }
+              }
+            }
+#pragma unroll
+            for (int p = 0; p < NP; p++)
+            {
+#pragma unroll
+              for (int k = 0; k < VW; k++)
+              {
+                if (j + p * LG < K)
+                {
+                  acc[p][k] = __fadd_rn(acc[p][k], l[p][k]);
                 }
               }
             }
