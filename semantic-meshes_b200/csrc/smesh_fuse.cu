@@ -1488,6 +1488,9 @@ __global__ void __launch_bounds__(256) get_kernel(const float* __restrict__ acc,
 {
   extern __shared__ __align__(16) float get_smem[];
   const int stride = Cpad + 1;
+  // e / C and i / chunks for e, i < 2^16 (a block of rows has at most 200 KB / 4 elements) as one multiply-high each:
+  // an integer division per element made this copy kernel issue-bound
+  const uint32_t magic_c = 0xFFFFFFFFu / (uint32_t) C + 1u, magic_chunks = 0xFFFFFFFFu / (uint32_t) (Cpad >> 2) + 1u;
   const int64_t nblocks = (P + rows - 1) / rows;
   for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x)
   {
@@ -1498,7 +1501,7 @@ __global__ void __launch_bounds__(256) get_kernel(const float* __restrict__ acc,
     for (int i = threadIdx.x; i < n * chunks; i += blockDim.x)
     {
       const float4 v = __ldcs(src + i);
-      const int r = i / chunks, j = i - r * chunks;
+      const int r = chunks == 1 ? i : (int) __umulhi((uint32_t) i, magic_chunks), j = i - r * chunks;
       float* d = get_smem + r * stride + 4 * j;
       d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
@@ -1520,14 +1523,14 @@ __global__ void __launch_bounds__(256) get_kernel(const float* __restrict__ acc,
         for (int k = 0; k < 4; k++)
         {
           const int e = 4 * i + k;
-          const int r = e / C;
+          const int r = C == 1 ? e : (int) __umulhi((uint32_t) e, magic_c);
           v[k] = get_smem[r * stride + (e - r * C)];
         }
         __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(v[0], v[1], v[2], v[3]));
       }
       for (int e = (total4 << 2) + threadIdx.x; e < total; e += blockDim.x)
       {
-        const int r = e / C;
+        const int r = C == 1 ? e : (int) __umulhi((uint32_t) e, magic_c);
         dst[e] = get_smem[r * stride + (e - r * C)];
       }
     }
@@ -1535,7 +1538,7 @@ __global__ void __launch_bounds__(256) get_kernel(const float* __restrict__ acc,
     {
       for (int e = threadIdx.x; e < total; e += blockDim.x)
       {
-        const int r = e / C;
+        const int r = C == 1 ? e : (int) __umulhi((uint32_t) e, magic_c);
         dst[e] = get_smem[r * stride + (e - r * C)];
       }
     }
@@ -1568,7 +1571,8 @@ static int launch_get(const float* acc, int64_t P, int C, float* out, cudaStream
   const int Cpad = smesh_fuse_padded_classes(C);
   // rows per CTA: 256 if they fit in ~96 KB (two CTAs per SM), else whatever fits in 200 KB, in whole warps
   const size_t row_bytes = (size_t) (Cpad + 1) * 4;
-  int rows = 256;
+  static const int env_rows = getenv("SMESH_GET_ROWS") ? atoi(getenv("SMESH_GET_ROWS")) : 0; // profiling only
+  int rows = (env_rows >= 32 && env_rows <= 1024) ? env_rows / 32 * 32 : 256;
   if (rows * row_bytes > 96 * 1024)
   {
     rows = (int) ((200 * 1024) / row_bytes) / 32 * 32;
