@@ -125,6 +125,32 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// shared -> global bulk copy in the issuing thread's current bulk group; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void bulk_commit_group()
+{
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// waits until at most N of the issuing thread's bulk groups have not yet READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read()
+{
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+// ... until at most N have not yet completed entirely
+template <int N>
+__device__ __forceinline__ void bulk_wait_group()
+{
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) accesses
 __device__ __forceinline__ void fence_proxy_async_smem()
 {

@@ -1478,7 +1478,8 @@ __device__ __forceinline__ void get_row(float* row, int C)
   }
 }
 
-// get(): HBM-bound (read P x Cpad, write P x C floats). A CTA stages `rows` accumulator rows in shared memory with
+// get(), staged (mul with C > 24, any kind with 200 < C <~ 1500, unaligned outputs; the streaming kernel below takes the
+// rest): HBM-bound (read P x Cpad, write P x C floats). A CTA stages `rows` accumulator rows in shared memory with
 // 128-bit coalesced loads (row stride Cpad + 1 words: a thread per row then walks its row without bank conflicts), one
 // thread per row turns it into the distribution in place in the reference's sequential order, and the block of rows
 // leaves as one contiguous run of rows * C floats with 128-bit coalesced stores.
@@ -1546,6 +1547,170 @@ __global__ void __launch_bounds__(256) get_kernel(const float* __restrict__ acc,
   }
 }
 
+// get() as a stream of bulk copies (C <= 200). Every WARP runs its own two-stage pipeline over blocks of 32 rows: one
+// bulk copy brings the block's 32 x Cpad floats into shared memory (mbarrier complete_tx), lane r turns row r into its
+// distribution - read with 128-bit shared loads (conflict-free when Cpad / 4 is odd, as for C = 19), in the reference's
+// sequential order - and writes it into a dense 32 x C staging block, which leaves as one shared -> global bulk copy
+// (bulk group; its buffer is reused once `wait_group.read` says it has been read). No __syncthreads, no address
+// arithmetic per element, the loads of the next two blocks always in flight.
+template <int VW>
+__device__ __forceinline__ void put_row(float* dst, const float (&v)[4], int c, int C)
+{
+  if (VW == 4)
+  {
+    *reinterpret_cast<float4*>(dst + c) = make_float4(v[0], v[1], v[2], v[3]); // (C % 4 == 0: whole chunks only)
+  }
+  else if (VW == 2)
+  {
+    *reinterpret_cast<float2*>(dst + c) = make_float2(v[0], v[1]);
+    if (c + 2 < C) *reinterpret_cast<float2*>(dst + c + 2) = make_float2(v[2], v[3]);
+  }
+  else
+  {
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+      if (c + k < C) dst[c + k] = v[k];
+    }
+  }
+}
+
+template <int KIND, int VW>
+__global__ void __launch_bounds__(128) get_stream_kernel(const float* __restrict__ acc, int64_t P, int C, int Cpad,
+                                                         float* __restrict__ out)
+{
+  extern __shared__ __align__(128) uint8_t get_stream_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int in_floats = 32 * Cpad, out_floats = 32 * C;            // (both multiples of 32 floats = 128 bytes)
+  float* base = reinterpret_cast<float*>(get_stream_smem) + (size_t) warp * 2 * (in_floats + out_floats);
+  float* in_buf[2] = {base, base + in_floats};
+  float* out_buf[2] = {base + 2 * in_floats, base + 2 * in_floats + out_floats};
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(get_stream_smem) + (size_t) nwarps * 2 * (in_floats + out_floats)) + 2 * warp;
+
+  const int64_t nblocks = (P + 31) / 32;
+  const int64_t stride = (int64_t) gridDim.x * nwarps;
+  int64_t blk = (int64_t) blockIdx.x * nwarps + warp;
+  const uint64_t policy = l2_evict_first_policy();
+  auto fetch = [&](int64_t b, int s) {
+    const int n = (int) min((int64_t) 32, P - b * 32);
+    const uint32_t bytes = (uint32_t) n * (uint32_t) Cpad * 4u;
+    mbar_arrive_expect_tx(bars + s, bytes);
+    bulk_g2s(in_buf[s], acc + (size_t) b * 32 * Cpad, bytes, bars + s, policy);
+  };
+  if (lane == 0)
+  {
+    mbar_init(bars, 1);
+    mbar_init(bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (blk < nblocks) fetch(blk, 0);
+    if (blk + stride < nblocks) fetch(blk + stride, 1);
+  }
+  __syncwarp();
+
+  const int chunks = Cpad >> 2;
+  uint32_t parity = 0;
+  int s = 0;
+  for (; blk < nblocks; blk += stride)
+  {
+    const int n = (int) min((int64_t) 32, P - blk * 32);
+    mbar_wait(bars + s, parity);
+    if (lane == 0)
+    {
+      bulk_wait_group_read<1>(); // the copy that left out_buf[s] two blocks ago has read it
+    }
+    __syncwarp();
+    if (lane < n)
+    {
+      float4* row = reinterpret_cast<float4*>(in_buf[s] + lane * Cpad);
+      float best = CUDART_INF_F;
+      bool have = false;
+      if (KIND == SMESH_KIND_MUL)
+      {
+        // max_el over LogProb = the smallest -log that is not "zero" (isinf), tt/numeric/LogProb.h
+        for (int j = 0; j < chunks; j++)
+        {
+          const float4 t = row[j];
+          const float v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+          {
+            if (4 * j + k < C && !isinf(v[k]) && (!have || v[k] < best))
+            {
+              best = v[k];
+              have = true;
+            }
+          }
+        }
+      }
+      // l1 norm: sequential sum of |v| from 0 (tt/tensor/linear_algebra/MiscOps.h:121-128)
+      float norm = 0.0f;
+      for (int j = 0; j < chunks; j++)
+      {
+        const float4 t = row[j];
+        float v[4] = {t.x, t.y, t.z, t.w};
+        if (KIND == SMESH_KIND_MUL)
+        {
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+          {
+            v[k] = (!have || isinf(v[k])) ? 0.0f : expf(-__fsub_rn(v[k], best));
+          }
+          row[j] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+          if (4 * j + k < C) norm = __fadd_rn(norm, fabsf(v[k]));
+        }
+      }
+      const float inv = __fdiv_rn(1.0f, norm);
+      float* dst = out_buf[s] + lane * C;
+      for (int j = 0; j < chunks; j++)
+      {
+        const float4 t = row[j];
+        float v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+          const float x = __fmul_rn(v[k], inv);
+          v[k] = (isnan(x) || isinf(x)) ? 0.0f : x; // Fusion.h:79-95
+        }
+        put_row<VW>(dst, v, 4 * j, C);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    float* gdst = out + (size_t) blk * 32 * C;
+    const uint32_t obytes = (uint32_t) n * (uint32_t) C * 4u;
+    if ((obytes & 15u) == 0u) // always for a full block (128 C bytes); the last block may not be
+    {
+      if (lane == 0)
+      {
+        bulk_s2g(gdst, out_buf[s], obytes);
+        bulk_commit_group();
+      }
+    }
+    else
+    {
+      for (int e = lane; e < n * C; e += 32)
+      {
+        gdst[e] = out_buf[s][e];
+      }
+      __syncwarp();
+    }
+    if (lane == 0 && blk + 2 * stride < nblocks)
+    {
+      fetch(blk + 2 * stride, s); // every lane has finished with in_buf[s] (the __syncwarp above)
+    }
+    if (s == 1) parity ^= 1u;
+    s ^= 1;
+  }
+  if (lane == 0)
+  {
+    bulk_wait_group<0>(); // shared memory must outlive the copies that read it
+  }
+}
+
 // class vectors too wide for the staged kernel: one thread per row straight from global memory
 template <int KIND>
 __global__ void __launch_bounds__(256) get_direct_kernel(const float* __restrict__ acc, int64_t P, int C, int Cpad,
@@ -1569,10 +1734,39 @@ template <int KIND>
 static int launch_get(const float* acc, int64_t P, int C, float* out, cudaStream_t stream)
 {
   const int Cpad = smesh_fuse_padded_classes(C);
+  static const bool no_stream = getenv("SMESH_GET_STAGED") != nullptr; // profiling only: the staged kernel below
+  // (mul: the exp() per element makes a lane's row walk the bottleneck once wide rows leave only a few warps per SM;
+  // measured at C = 40 / 150: 60 / 1264 us against 46 / 1080 us of the staged kernel, at C = 19 79 against 88)
+  const int stream_max_c = KIND == SMESH_KIND_MUL ? 24 : 200;
+  if (C <= stream_max_c && !no_stream && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(acc) & 15) == 0)
+  {
+    // warps per CTA so that a CTA stays below ~100 KB (two or more CTAs per SM): 4 up to C = 48, 2 up to 100, else 1
+    const size_t warp_bytes = (size_t) 2 * 32 * (Cpad + C) * 4;
+    const int warps = warp_bytes * 4 <= 100 * 1024 ? 4 : (warp_bytes * 2 <= 100 * 1024 ? 2 : 1);
+    const size_t smem = warps * warp_bytes + (size_t) warps * 16;
+    void (*kernel)(const float*, int64_t, int, int, float*) =
+      C % 4 == 0 ? get_stream_kernel<KIND, 4> : (C % 2 == 0 ? get_stream_kernel<KIND, 2> : get_stream_kernel<KIND, 1>);
+    int blocks_per_sm = 0;
+    const int rc = kernel_blocks_per_sm(reinterpret_cast<const void*>(kernel), warps * 32, smem, &blocks_per_sm);
+    if (rc != SMESH_OK)
+    {
+      return rc;
+    }
+    if (blocks_per_sm >= 1)
+    {
+      int64_t blocks = ((P + 31) / 32 + warps - 1) / warps;
+      const int64_t cap = (int64_t) num_sms() * blocks_per_sm;
+      if (blocks > cap) blocks = cap;
+      if (blocks < 1) return SMESH_OK;
+      kernel<<<(unsigned) blocks, warps * 32, smem, stream>>>(acc, P, C, Cpad, out);
+      SMESH_LAUNCH_CHECK("get_stream_kernel");
+      return SMESH_OK;
+    }
+  }
   // rows per CTA: 256 if they fit in ~96 KB (two CTAs per SM), else whatever fits in 200 KB, in whole warps
   const size_t row_bytes = (size_t) (Cpad + 1) * 4;
   static const int env_rows = getenv("SMESH_GET_ROWS") ? atoi(getenv("SMESH_GET_ROWS")) : 0; // profiling only
-  int rows = (env_rows >= 32 && env_rows <= 1024) ? env_rows / 32 * 32 : 256;
+  int rows = (env_rows >= 32 && env_rows <= 1024) ? env_rows / 32 * 32 : (Cpad >= 32 ? 128 : 256); // (C = 40: 35 us against 39)
   if (rows * row_bytes > 96 * 1024)
   {
     rows = (int) ((200 * 1024) / row_bytes) / 32 * 32;

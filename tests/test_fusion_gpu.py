@@ -688,6 +688,27 @@ def test_get_kernel_shapes(sm, kind, C):
         assert_get_close(kind, got, ref.get())
 
 
+@pytest.mark.parametrize("kind", ["sum", "mul"])
+@pytest.mark.parametrize("C", [19, 6, 8, 150])
+def test_get_stream_pipeline_many_blocks(sm, kind, C):
+    """get() for C <= 200 streams blocks of 32 rows through a two-stage bulk-copy pipeline per warp: enough rows that every
+    warp takes several blocks and reuses both stages (and a last block of 1 row), against the oracle's get(); also from
+    an accumulator slice that starts at row 1."""
+    rng = np.random.default_rng(C + 100)
+    P = (400_001 if C < 100 else 60_001)
+    acc = np.abs(rng.normal(size=(P, C))).astype(np.float32)
+    acc[rng.random(P) < 0.2] = 0
+    if kind == "mul":
+        acc[rng.random((P, C)) < 0.05] = np.inf
+    agg, ref = sm.fusion.MeshAggregator(P, C, kind), oracle.Aggregator(P, C, kind)
+    agg.load_state(acc)
+    ref.acc[...] = acc
+    exp = ref.get()
+    assert_get_close(kind, agg.get(), exp)
+    part = agg.get(rows=(1, P))
+    assert_get_close(kind, part, exp[1:])
+
+
 def test_mul_direct_form_matches_reference_sequence(sm, monkeypatch):
     """mul accumulates -log(p^w). The kernels use -w log p where p^w stays a normal float and the reference's own
     powf + logf sequence elsewhere (underflow to the absorbing zero, p = 0, w = 0); SMESH_MUL_EXACT=1 forces the reference's
