@@ -380,7 +380,7 @@ def run_ours(args, cfg):
         parity = check_parity(scene, kinds=("sum", "summax", "mul") if rank == 0 else ("sum",))
     agg = semantic_meshes.fusion.MeshAggregator(primitives=P, classes=C)
     pipe = ViewPipeline(renderer, agg, fused_count=args.fused_count, count_ahead=args.count_ahead, write_depth=True,
-                        group=args.group, count_stream=args.count_stream)
+                        group=args.group, count_stream=args.count_stream, lanes=args.lanes)
     strong = args.scaling == "strong"
     if strong:
         # the config's own job: cfg["views"] views dealt round-robin; a rank cycles its B resident views to make up its share
@@ -628,7 +628,7 @@ def run_ours(args, cfg):
                    "cache": f"{B} distinct views of {scene.bytes_inputs / 1e6:.0f} MB cycled (>> 126 MB L2)",
                    "cuda_graph": graph is not None, "allreduce_in_timed_region": world > 1,
                    "render_add_overlap": not args.no_overlap, "fused_count": bool(args.fused_count),
-                   "views_per_add_batch": args.group,
+                   "views_per_add_batch": args.group, "fusion_lanes": args.lanes,
                    "timed_region_ms": elapsed_ms},
         "mpixel_face_scatters_per_s": value * float(np.mean(scene.accepted)) / 1e6,
         "stages": stages,
@@ -813,6 +813,7 @@ def main():
     ap.add_argument("--fused-count", action="store_true", help="count the view's pixels per face in the render pass (N2)")
     ap.add_argument("--count-ahead", action="store_true", help="pipeline: the count of view v+1 rides in the scatter of view v")
     ap.add_argument("--count-stream", action="store_true", help="pipeline: the count stage on a third stream")
+    ap.add_argument("--lanes", type=int, default=1, help="pipeline: 2 = adds alternate between two fusion streams")
     ap.add_argument("--group", type=int, default=1, help="pipeline: views per add_batch call (1 = one add per view)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity checks (profiling runs only)")

@@ -215,9 +215,14 @@ int smesh_fuse_scatter_count_next(int kind, const uint32_t* ids32, const float* 
  * A batch of B views with identical shapes, view b at ids + b*ids_stride_view (elements), probs + b*probs_stride_view
  * (floats), weights + b*w_stride_view (floats, if weights != NULL). Equivalent to B calls of smesh_fuse_add in order with
  * epochs count_epoch0, count_epoch0 + 1, ... (all <= 255), or all 0.
+ * (the ORDER of the float additions into a row is not defined, exactly as between two pixels of one view).
  *   counts2  uint32[2][P]: TWO counter arrays; the view with epoch e counts into array e & 1 (epoch 0: array 0 only).
- *            With tagged epochs and 32-bit flat ids the count stage of view b+1 rides in the scatter launch of view b
- *            (one extra warp per CTA of the ring kernels), so a batch costs one count launch plus B scatter launches.
+ *            With tagged epochs and 32-bit flat ids the views are dealt to two lanes - `stream` and a side stream owned by
+ *            the library (per host thread and device), forked from and joined to `stream` by events, so the call is
+ *            stream-ordered on `stream` and can be captured into a CUDA graph - and each lane runs count + scatter of its
+ *            views on its own counter array: one lane's count stage, launch gaps and tails are covered by the other's
+ *            scatter. If the side stream does not exist yet while `stream` is being captured (nothing is created during a
+ *            capture): one stream, the count stage of view b+1 riding in the scatter launch of view b.
  */
 int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id_dtype, int64_t ids_stride_view,
                          int64_t ids_stride_outer, int64_t ids_stride_inner, const float* probs,

@@ -2150,6 +2150,51 @@ struct ViewStages
   }
 };
 
+// The side stream of smesh_fuse_add_batch's second lane and its fork / join events: one set per host thread and device
+// (two host threads batching on one device must not share events). NULL while the caller's stream is being captured and
+// the set does not exist yet (nothing is created during a capture), or if creation fails: the caller then takes the
+// single-stream path.
+struct BatchLane
+{
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+
+static BatchLane* batch_lane(cudaStream_t stream)
+{
+  constexpr int MAX_DEVICES = 64;
+  thread_local BatchLane lanes[MAX_DEVICES];
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES)
+  {
+    cudaGetLastError();
+    return nullptr;
+  }
+  BatchLane& l = lanes[dev];
+  if (l.side == nullptr)
+  {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone)
+    {
+      cudaGetLastError();
+      return nullptr;
+    }
+    BatchLane fresh;
+    if (cudaStreamCreateWithFlags(&fresh.side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fresh.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fresh.join, cudaEventDisableTiming) != cudaSuccess)
+    {
+      cudaGetLastError();
+      if (fresh.join) cudaEventDestroy(fresh.join);
+      if (fresh.fork) cudaEventDestroy(fresh.fork);
+      if (fresh.side) cudaStreamDestroy(fresh.side);
+      return nullptr;
+    }
+    l = fresh;
+  }
+  return &l;
+}
+
 static int make_view(const char* fn, ViewStages& v, int kind, const void* ids, int id_dtype, int64_t ids_so, int64_t ids_si,
                      const float* probs, const float* weights, int64_t w_so, int64_t w_si, int64_t n_outer, int64_t n_inner,
                      int C, int64_t P, float iew, uint32_t* ids32, float* acc, uint32_t epoch)
@@ -2408,6 +2453,45 @@ extern "C" int smesh_fuse_add_batch(int kind, int64_t B, const void* ids, int id
   // tagged mode: view b counts into array (epoch & 1); untagged mode: array 0 only (it is clean again after every view)
   auto epoch_of = [&](int64_t b) -> uint32_t { return count_epoch0 != 0 ? count_epoch0 + (uint32_t) b : 0u; };
   auto counts_of = [&](int64_t b) -> uint32_t* { return counts2 + (size_t) (epoch_of(b) & 1u) * (size_t) P; };
+
+  // Two lanes: with tagged counters and ids consumed in place, the views alternate between the caller's stream and a side
+  // stream of this library (forked from / joined to the caller's stream by events, so the call stays stream-ordered and
+  // capturable). Each lane runs count(b) -> scatter(b) of its views on its own counter array (array = epoch parity = lane);
+  // the accumulator is shared (atomic reductions commute). One lane's count stage, launch gap, ramp-up and tail are
+  // covered by the other lane's scatter kernel: measured 36.3 us per view at cfg3 against 39.6 us with the riding count
+  // below and 43.5 us for one add() per view (cfg5: 18.2 / 21.4 / 23.1), tools/time_two_streams.py.
+  const bool no_lanes = getenv("SMESH_NO_BATCH_LANES") != nullptr; // profiling / tests: the single-stream path below
+  if (B >= 2 && count_epoch0 != 0 && !no_lanes)
+  {
+    ViewStages probe;
+    rc = view(0, probe);
+    if (rc != SMESH_OK)
+    {
+      return rc;
+    }
+    BatchLane* lane = probe.zero_copy ? batch_lane(stream) : nullptr;
+    if (lane != nullptr)
+    {
+      SMESH_CUDA_CHECK(cudaEventRecord(lane->fork, stream));
+      SMESH_CUDA_CHECK(cudaStreamWaitEvent(lane->side, lane->fork, 0));
+      for (int64_t b = 0; b < B; b++)
+      {
+        ViewStages v;
+        rc = view(b, v);
+        cudaStream_t st = (b & 1) ? lane->side : stream;
+        if (rc == SMESH_OK) rc = v.count(counts_of(b), epoch_of(b), st);
+        if (rc == SMESH_OK) rc = v.scatter(counts_of(b), epoch_of(b), st);
+        if (rc != SMESH_OK)
+        {
+          break;
+        }
+      }
+      // (join even after an error: the caller's stream must not run ahead of work already queued on the side stream)
+      SMESH_CUDA_CHECK(cudaEventRecord(lane->join, lane->side));
+      SMESH_CUDA_CHECK(cudaStreamWaitEvent(stream, lane->join, 0));
+      return rc;
+    }
+  }
 
   static const bool no_overlap = getenv("SMESH_NO_BATCH_OVERLAP") != nullptr; // profiling only
   // The count stage of view b+1 rides in the scatter launch of view b (one extra warp per CTA of the ring kernels, see

@@ -15,7 +15,7 @@ from . import _lib
 
 class ViewPipeline:
     def __init__(self, renderer, aggregator, fused_count=False, count_ahead=False, write_depth=False, group=1,
-                 count_stream=False):
+                 count_stream=False, lanes=1):
         torch = _lib.require_cuda()
         self.fused_count = bool(fused_count)
         # count_ahead: the count stage of view v+1 rides in the scatter launch of view v (MeshAggregator.add(count_next=)).
@@ -31,11 +31,19 @@ class ViewPipeline:
         self.count_stream = bool(count_stream)
         # group: views per add_batch call (1 = one add per view); needs predictions that form a regular batch in memory
         self.group = max(1, int(group))
+        # lanes: 2 = the adds alternate between the caller's stream and a second fusion stream (views v and v+1 use
+        # different counter arrays of the aggregator, so their count + scatter stages are independent; the accumulator
+        # updates are atomic and commute): one view's count stage, launch gaps and tail run under the other's scatter.
+        # Off by default: that is what makes add_batch 9 % faster on its own, but under the renderer the SMs have no idle
+        # time left to fill - measured 11.1 k against 12.6 k views/s at config 3 (12.3 k with a high-priority render
+        # stream), profiles/r02ad_pipeline_lanes.txt
+        self.lanes = 2 if int(lanes) == 2 and not (self.fused_count or self.count_ahead or self.count_stream) else 1
         self._torch = torch
         self.renderer, self.aggregator = renderer, aggregator
         with torch.cuda.device(renderer.device):
             self._render_stream = torch.cuda.Stream()
             self._count_stream = torch.cuda.Stream() if self.count_stream else None
+            self._fuse_stream2 = torch.cuda.Stream() if self.lanes == 2 else None
 
     def run(self, cameras, predictions, weights=None, keep_indices=False):
         """cameras: sequence of data.Camera; predictions: sequence (or batched tensor) of (W, H, C) float32 arrays, one per
@@ -53,6 +61,9 @@ class ViewPipeline:
         n = len(cameras)
         fused = self.fused_count and self.aggregator.primitives == self.renderer.getPrimitivesNum()
         added = []  # events: add of view v enqueued (the counter array of view v is free again after it)
+        fuse = [main] if self._fuse_stream2 is None else [main, self._fuse_stream2]
+        for f in fuse[1:]:
+            f.wait_stream(main)
         for v in range(n + 1):
             nxt = None
             if v < n:
@@ -76,22 +87,27 @@ class ViewPipeline:
                 nxt = (idx, ev)
             if pending is not None:
                 idx_prev, ev_prev = pending
-                main.wait_event(ev_prev)
+                f = fuse[(v - 1) % len(fuse)]
+                f.wait_event(ev_prev)
                 ride = None
                 if self.count_ahead and not fused and nxt is not None:
                     # the fusion of view v-1 waits for the render of view v as well and counts it on the way (the renderer
                     # is then two views ahead of the fusion instead of one: same throughput, one launch less per view)
-                    main.wait_event(nxt[1])
+                    f.wait_event(nxt[1])
                     ride = nxt[0]
-                    ride.record_stream(main)
-                self.aggregator.add(idx_prev, predictions[v - 1], None if weights is None else weights[v - 1], count_next=ride)
-                idx_prev.record_stream(main)
+                    ride.record_stream(f)
+                with torch.cuda.stream(f):
+                    self.aggregator.add(idx_prev, predictions[v - 1], None if weights is None else weights[v - 1],
+                                        count_next=ride)
+                idx_prev.record_stream(f)
                 ev_add = torch.cuda.Event()
-                ev_add.record(main)
+                ev_add.record(f)
                 added.append(ev_add)
                 if keep_indices:
                     kept.append(idx_prev)
             pending = nxt
+        for f in fuse[1:]:
+            main.wait_stream(f)
         rs.wait_stream(main)  # the renderer's workspace / outputs are not reused before the last add has been enqueued
         if self._count_stream is not None:
             main.wait_stream(self._count_stream)

@@ -570,12 +570,16 @@ def test_count_stage_on_rendered_ids(sm):
         assert np.array_equal(got, np.bincount(ids[ids < P].astype(np.int64), minlength=P))
 
 
+@pytest.mark.parametrize("lanes", [True, False])
 @pytest.mark.parametrize("kind", KINDS)
-def test_add_batch_overlapped_and_captured(sm, kind):
-    """add_batch runs the count stage of view b+1 on a side stream under the scatter stage of view b (two counter arrays):
-    same accumulator as the sequential loop, also with weights, also when the call is captured into a CUDA graph and
-    replayed, and for odd / even batch sizes."""
+def test_add_batch_overlapped_and_captured(sm, kind, lanes, monkeypatch):
+    """add_batch deals the views to two lanes (the caller's stream and a side stream of the library, one counter array
+    each); without lanes (SMESH_NO_BATCH_LANES, or when the side stream would have to be created during a capture) the
+    count stage of view b+1 rides in the scatter launch of view b. Either way: same accumulator as the sequential loop,
+    also with weights, also when the call is captured into a CUDA graph and replayed, and for odd / even batch sizes."""
     import torch
+    if not lanes:
+        monkeypatch.setenv("SMESH_NO_BATCH_LANES", "1")
     rng = np.random.default_rng(55)
     W, H, C, P = 96, 130, 19, 400
     for B in (2, 5, 8):
