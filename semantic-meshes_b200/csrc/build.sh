@@ -8,7 +8,7 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 COMMON="-std=c++17 -O3 -lineinfo $ARCH -Xcompiler -fPIC ${SMESH_NVCC_EXTRA:-}"
 mkdir -p "$HERE/build"
 # stale objects must never be linked if a compile fails
-rm -f "$HERE/build/smesh_api.o" "$HERE/build/smesh_raster.o" "$HERE/build/smesh_fuse.o"
+rm -f "$HERE/build/smesh_api.o" "$HERE/build/smesh_raster.o" "$HERE/build/smesh_fuse.o" "$HERE/build/smesh_pipeline.o"
 pids=()
 $NVCC $COMMON -c "$HERE/smesh_api.cu" -o "$HERE/build/smesh_api.o" &
 pids+=($!)
@@ -17,8 +17,10 @@ $NVCC $COMMON -fmad=false -Xcompiler -fopenmp -c "$HERE/smesh_raster.cu" -o "$HE
 pids+=($!)
 $NVCC $COMMON -c "$HERE/smesh_fuse.cu" -o "$HERE/build/smesh_fuse.o" &
 pids+=($!)
+$NVCC $COMMON -c "$HERE/smesh_pipeline.cu" -o "$HERE/build/smesh_pipeline.o" &
+pids+=($!)
 for pid in "${pids[@]}"; do
   wait "$pid" || { echo "build.sh: a compile job failed" >&2; exit 1; }
 done
-$NVCC $ARCH -shared -o "$OUT" "$HERE/build/smesh_api.o" "$HERE/build/smesh_raster.o" "$HERE/build/smesh_fuse.o" -lcudart -lgomp
+$NVCC $ARCH -shared -o "$OUT" "$HERE/build/smesh_api.o" "$HERE/build/smesh_raster.o" "$HERE/build/smesh_fuse.o" "$HERE/build/smesh_pipeline.o" -lcudart -lgomp
 echo "built $OUT"

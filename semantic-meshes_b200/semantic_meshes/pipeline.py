@@ -10,12 +10,15 @@ stream, then ONE `add_batch` of the group on the fusion stream (one count launch
 scatter launches) while the next group renders. The results are identical to the sequential README loop
 (`idx, _ = renderer.render(cam); aggregator.add(idx, probs)`).
 """
+import ctypes
+import os
+
 from . import _lib
 
 
 class ViewPipeline:
     def __init__(self, renderer, aggregator, fused_count=False, count_ahead=False, write_depth=False, group=1,
-                 count_stream=False, lanes=1):
+                 count_stream=False, lanes=1, native=True):
         torch = _lib.require_cuda()
         self.fused_count = bool(fused_count)
         # count_ahead: the count stage of view v+1 rides in the scatter launch of view v (MeshAggregator.add(count_next=)).
@@ -38,6 +41,14 @@ class ViewPipeline:
         # time left to fill - measured 11.1 k against 12.6 k views/s at config 3 (12.3 k with a high-priority render
         # stream), profiles/r02ad_pipeline_lanes.txt
         self.lanes = 2 if int(lanes) == 2 and not (self.fused_count or self.count_ahead or self.count_stream) else 1
+        # native: the loop is enqueued by the library (smesh_pipeline_views) whenever the inputs qualify (_run_native) and no
+        # other mode is selected
+        self.native = bool(native) and not (self.fused_count or self.count_ahead or self.count_stream) and self.group == 1 \
+            and self.lanes == 1
+        # index images in flight in the native loop (with 2 the renderer waits for the fusion of the view before last and
+        # the two streams fall into lock step: 11.0 k against 12.6 k views/s at config 3)
+        self.ring = max(1, min(8, int(os.environ.get("SMESH_PIPELINE_RING", "4"))))
+        self._ring = self._depth_ring = None
         self._torch = torch
         self.renderer, self.aggregator = renderer, aggregator
         with torch.cuda.device(renderer.device):
@@ -49,6 +60,8 @@ class ViewPipeline:
         """cameras: sequence of data.Camera; predictions: sequence (or batched tensor) of (W, H, C) float32 arrays, one per
         camera; weights: optional sequence of (W, H) float32. Returns the list of index images if keep_indices."""
         torch = self._torch
+        if self.native and not keep_indices and len(cameras) > 0 and self._run_native(cameras, predictions, weights):
+            return None
         if self.group > 1 and not self.fused_count and len(cameras) > 0:
             done = self._run_grouped(cameras, predictions, weights, keep_indices)
             if done is not False:
@@ -112,6 +125,70 @@ class ViewPipeline:
         if self._count_stream is not None:
             main.wait_stream(self._count_stream)
         return kept if keep_indices else None
+
+    def _run_native(self, cameras, predictions, weights):
+        """The same loop enqueued by the library (smesh_pipeline_views: one C call per <= 200 views instead of ~10 Python
+        level calls per view - the per-view host time of the loop above is ~90 us, more than the GPU needs). -> False if
+        the inputs do not qualify: views of one resolution below 2^24 pixels, predictions (and weights) that are contiguous,
+        16-byte aligned float32 tensors on the aggregator's device, a plain triangle renderer."""
+        import numpy as np
+        from .render import TriangleRenderer
+        torch = self._torch
+        ren, agg = self.renderer, self.aggregator
+        if type(ren) is not TriangleRenderer or ren.device != agg.device or ren._F == 0 or agg.primitives == 0:
+            return False
+        n = len(cameras)
+        W, H = cameras[0].resolution
+        if W < 1 or H < 1 or W * H >= (1 << 24) or any(c.resolution != (W, H) for c in cameras):
+            return False
+        C = agg.classes
+        if len(predictions) != n or (weights is not None and len(weights) != n):
+            return False
+        shape_p, shape_w, f32 = (W, H, C), (W, H), torch.float32
+        pp = (ctypes.c_void_p * n)()
+        for i in range(n):
+            p = predictions[i]
+            if (not isinstance(p, torch.Tensor) or p.dtype != f32 or tuple(p.shape) != shape_p or p.device != agg.device
+                    or not p.is_contiguous()):
+                return False
+            pp[i] = p.data_ptr()
+            if pp[i] % 16 != 0:
+                return False
+        wp = None
+        if weights is not None:
+            wp = (ctypes.c_void_p * n)()
+            for i in range(n):
+                w = weights[i]
+                if (not isinstance(w, torch.Tensor) or w.dtype != f32 or tuple(w.shape) != shape_w or w.device != agg.device
+                        or not w.is_contiguous()):
+                    return False
+                wp[i] = w.data_ptr()
+        ptr = ctypes.sizeof(ctypes.c_void_p)
+        R = np.ascontiguousarray(np.stack([np.asarray(c.rotation, dtype=np.float32).reshape(9) for c in cameras]))
+        t = np.ascontiguousarray(np.stack([np.asarray(c.translation, dtype=np.float32).reshape(3) for c in cameras]))
+        f = np.ascontiguousarray(np.stack([np.asarray(c.focal_lengths, dtype=np.float64).reshape(2) for c in cameras]))
+        c0 = np.ascontiguousarray(np.stack([np.asarray(c.principal_point, dtype=np.float64).reshape(2) for c in cameras]))
+        with _lib.on_device(torch, ren._dev_index):
+            ws = ren._ensure_workspace(W, H)
+            nring = self.ring
+            if self._ring is None or tuple(self._ring.shape) != (nring, W, H):
+                self._ring = torch.empty((nring, W, H), dtype=torch.int32, device=ren.device)
+                self._depth_ring = torch.empty((nring, W, H), dtype=torch.float32, device=ren.device) if self.write_depth else None
+            stream = _lib.raw_stream(torch, ren._dev_index)
+            first = 0
+            while first < n:
+                k = min(200, n - first)
+                epoch0 = agg._next_epochs(W * H, k)
+                rc = _lib.lib.smesh_pipeline_views(
+                    ren._mesh_ptr, ren._mesh_bytes, ren._V, ren._F, k, R[first:].ctypes.data, t[first:].ctypes.data,
+                    f[first:].ctypes.data, c0[first:].ctypes.data, W, H, ws.data_ptr(), ws.numel(), nring, self._ring.data_ptr(),
+                    self._depth_ring.data_ptr() if self._depth_ring is not None else None, agg._kind,
+                    ctypes.addressof(pp) + first * ptr, ctypes.addressof(wp) + first * ptr if wp is not None else None,
+                    C, agg.primitives, agg.images_equal_weight, agg._counts2.data_ptr(), epoch0, agg._acc.data_ptr(),
+                    stream)
+                _lib.check(rc)
+                first += k
+        return True
 
     @staticmethod
     def _as_batch(torch, items, first, k):

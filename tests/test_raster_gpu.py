@@ -604,6 +604,83 @@ def test_pipeline_count_ahead_matches_sequential(sm):
     torch.testing.assert_close(ovl.state(), 2 * seq.state(), rtol=1e-5, atol=1e-6)
 
 
+def test_native_pipeline_matches_sequential(sm):
+    """ViewPipeline's default path hands the whole loop to the library (smesh_pipeline_views: renders on a side stream one
+    view ahead, two index images used alternately): same accumulator as the sequential README loop and as the Python-level
+    pipeline (native=False) - for all kinds, with weights, with predictions as a batched tensor or as a list with repeats,
+    over 450 views (chunks of 200, the 8-bit count epoch wraps), captured into a CUDA graph and replayed; host
+    predictions fall back to the Python-level loop."""
+    import torch
+    from semantic_meshes import synthetic
+    from semantic_meshes.pipeline import ViewPipeline
+    W, H, C = 160, 120, 19
+    mesh = synthetic.mesh("terrain", 6000, seed=2)
+    renderer = sm.render.triangles(mesh)
+    P = renderer.getPrimitivesNum()
+    cams = synthetic.terrain_cameras(7, W, H, 6000, tris_per_view=1500, seed=8)
+    n = len(cams)
+    preds = torch.stack([synthetic.predictions_torch(W, H, C, seed=v, device="cuda") for v in range(n)])
+    wts = torch.rand((n, W, H), device="cuda") * 2
+    for kind in ("sum", "summax", "mul"):
+        seq, nat, py = (sm.fusion.MeshAggregator(P, C, kind) for _ in range(3))
+        for v, cam in enumerate(cams):
+            idx, _ = renderer.render(cam)
+            seq.add(idx, preds[v], wts[v])
+        pipe = ViewPipeline(renderer, nat)
+        assert pipe.native
+        assert pipe._run_native(cams, preds, wts) is True            # (the inputs qualify: run() would not fall back)
+        nat.reset()
+        pipe.run(cams, preds, wts)
+        ViewPipeline(renderer, py, native=False).run(cams, preds, wts)
+        torch.cuda.synchronize()
+        fin = torch.isfinite(seq.state())
+        assert torch.equal(fin, torch.isfinite(nat.state())) and torch.equal(fin, torch.isfinite(py.state()))
+        torch.testing.assert_close(nat.state()[fin], seq.state()[fin], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(py.state()[fin], seq.state()[fin], rtol=1e-5, atol=1e-6)
+    # a long list with repeats, no weights, write_depth: 450 views = 64 x the 7 views + 2
+    seq, nat = sm.fusion.MeshAggregator(P, C), sm.fusion.MeshAggregator(P, C)
+    for v, cam in enumerate(cams):
+        idx, _ = renderer.render(cam)
+        seq.add(idx, preds[v])
+    once = seq.state().clone()
+    seq.add(renderer.render(cams[0])[0], preds[0])
+    seq.add(renderer.render(cams[1])[0], preds[1])
+    extra = seq.state() - once
+    order = [v % n for v in range(450)]
+    pipe = ViewPipeline(renderer, nat, write_depth=True)
+    pipe.run([cams[v] for v in order], [preds[v] for v in order])
+    torch.cuda.synchronize()
+    torch.testing.assert_close(nat.state(), 64 * once + extra, rtol=2e-5, atol=1e-5)
+    # captured into a CUDA graph (the side stream exists by now) and replayed
+    g_agg = sm.fusion.MeshAggregator(P, C)
+    g_pipe = ViewPipeline(renderer, g_agg)
+    g_pipe.run(cams, preds)
+    torch.cuda.synchronize()
+    g_agg.reset()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_agg.restart_epochs()
+        g_pipe.run(cams, preds)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(g_agg.state(), 3 * once, rtol=1e-5, atol=1e-6)
+    # host predictions do not qualify: the Python-level loop takes over
+    h_agg = sm.fusion.MeshAggregator(P, C)
+    h_pipe = ViewPipeline(renderer, h_agg)
+    host = [preds[v].cpu().numpy() for v in range(n)]
+    assert h_pipe._run_native(cams, host, None) is False
+    h_pipe.run(cams, host)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(h_agg.state(), once, rtol=1e-5, atol=1e-6)
+    # the renderer is usable on the caller's stream right after a native run (its workspace was used on the side stream)
+    idx_after, _ = renderer.render(cams[3])
+    pipe.run(cams, preds)
+    idx_again, _ = renderer.render(cams[3])
+    torch.cuda.synchronize()
+    assert torch.equal(idx_after, idx_again)
+
+
 def test_pipeline_grouped_matches_sequential(sm):
     """ViewPipeline(group=K): K renders into one index buffer, one add_batch per group - with a batched prediction tensor,
     with a list of slices of one (regular batch: no copy), with a list of separate tensors (falls back to one add per
