@@ -649,7 +649,7 @@ def run_ours(args, cfg):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src,
                      "timing": f"whole add: smesh_fuse_add_batch over {B} views in a CUDA graph, CUDA events / views "
-                               "(count of view b+1 on a side stream under the scatter of view b)",
+                               "(views dealt to two lanes: the caller's stream and a side stream of the library, one counter array each)",
                      "algorithmic_bytes_per_launch": scene.bytes_add,
                      "input_only_frac": scene.bytes_inputs / add_s / 1e9 / peak,
                      "frac_add_serial": scene.bytes_add / (stages["add_ms_per_view_serial"] * 1e-3) / 1e9 / peak,

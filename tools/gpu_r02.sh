@@ -32,5 +32,7 @@ if [ "${3:-}" = "ncu" ]; then
     python tools/prof_driver.py cfg3 4 > $OUT/add_full.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:raster_unit -s 4 -c 1 -o $OUT/raster_full \
     python tools/prof_driver.py cfg3 4 > $OUT/raster_full.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:get_stream -c 1 -o $OUT/get_full \
+    python tools/prof_driver.py cfg3 4 > $OUT/get_full.log 2>&1
 fi
 ls -la $OUT
