@@ -252,6 +252,15 @@ int smesh_fuse_labels(const float* dist, int64_t P, int C, float dont_care_thres
 int smesh_fuse_render(const void* annotations, int64_t P, int elem_bytes, const uint32_t* ids32, int64_t n_pix,
                       const void* background, void* out, void* stream);
 
+/*
+ * Self-test (used by tests/): the rasterizer normalises a pixel's ray with 1 / sqrt(l2), both operations IEEE
+ * round-to-nearest (MiscOps.h:125-128), l2 >= 1. The kernels evaluate that with the fast paths of nvcc's own expansion
+ * of sqrt.rn and rcp.rn written out without their range checks. This entry compares the two for the n floats whose bit
+ * patterns start at first_bits (first_bits + n <= 0x7F800000) and leaves the number of differing results in
+ * *mismatches_dev (device uint64): 0 for every float in [1, 2^100).
+ */
+int smesh_selftest_inv_sqrt(uint32_t first_bits, uint64_t n, uint64_t* mismatches_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * The per-view loop of the reference's scripts, `idx, depth = renderer.render(cam); aggregator.add(idx, probs)`
  * (python/scripts/colorize_mesh.py:60-72), for B views of one resolution enqueued by ONE call: equivalent to

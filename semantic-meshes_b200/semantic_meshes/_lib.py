@@ -40,6 +40,7 @@ SIGNATURES = {
     "smesh_fuse_get": (_int, [_int, _vp, _i64, _int, _vp, _vp]),
     "smesh_fuse_labels": (_int, [_vp, _i64, _int, _f32, _vp, _vp]),
     "smesh_fuse_render": (_int, [_vp, _i64, _int, _vp, _i64, _vp, _vp, _vp]),
+    "smesh_selftest_inv_sqrt": (_int, [_u32, ctypes.c_uint64, _vp, _vp]),
     "smesh_pipeline_views": (_int, [_vp, _sz, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _int, _vp, _vp, _int,
                                     _vp, _vp, _int, _i64, _f32, _vp, _u32, _vp, _vp]),
 }

@@ -604,6 +604,20 @@ def test_pipeline_count_ahead_matches_sequential(sm):
     torch.testing.assert_close(ovl.state(), 2 * seq.state(), rtol=1e-5, atol=1e-6)
 
 
+def test_inv_sqrt_fast_path_is_exact_for_every_float(sm):
+    """The ray normalisation 1 / sqrt(l2) (IEEE sqrt, IEEE reciprocal; l2 >= 1) is evaluated without the range checks of
+    nvcc's expansion: bit-identical to __frcp_rn(__fsqrt_rn(x)) for EVERY float in [1, 2^100) - 838 860 800 values."""
+    import torch
+    from semantic_meshes import _lib
+    out = torch.zeros(1, dtype=torch.int64, device="cuda")
+    first, last = 0x3F800000, 0x3F800000 + 100 * (1 << 23)      # 1.0 ... 2^100
+    _lib.check(_lib.lib.smesh_selftest_inv_sqrt(first, last - first, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    assert int(out.item()) == 0
+    # (the self-test itself can fail: below 2^-100 the fast path is not the library's)
+    _lib.check(_lib.lib.smesh_selftest_inv_sqrt(0x00000001, 1 << 23, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    assert int(out.item()) > 0
+
+
 def test_native_pipeline_matches_sequential(sm):
     """ViewPipeline's default path hands the whole loop to the library (smesh_pipeline_views: renders on a side stream one
     view ahead, two index images used alternately): same accumulator as the sequential README loop and as the Python-level
