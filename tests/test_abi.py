@@ -49,6 +49,19 @@ def test_workspace_bytes_and_errors():
     assert m.value >= 642 * 16 + 1280 * 16 + 10 * 16 and t.value >= 1280 * 24
     assert _lib.lib.smesh_raster_mesh_bytes(-1, 5, ctypes.byref(m), ctypes.byref(t)) == _lib.ERR_INVALID_ARGUMENT
     assert _lib.lib.smesh_raster_mesh_build(None, 3, None, 1, None, 0, None, 0, None) == _lib.ERR_INVALID_ARGUMENT
+    # the one-call view loop: null buffers, a ring outside 1..8, count epochs that would leave 1..255
+    dummy = ctypes.c_void_p(16)
+    def views(B, ring, epoch0, buf):
+        return _lib.lib.smesh_pipeline_views(buf, 64, 3, 1, B, buf, buf, buf, buf, 4, 4, buf, 64, ring, buf, None, 0, buf, None,
+                                             3, 1, 0.5, buf, epoch0, buf, None)
+    assert views(2, 4, 1, None) == _lib.ERR_INVALID_ARGUMENT
+    assert views(2, 0, 1, dummy) == _lib.ERR_INVALID_ARGUMENT
+    assert views(2, 9, 1, dummy) == _lib.ERR_INVALID_ARGUMENT
+    assert views(2, 4, 0, dummy) == _lib.ERR_INVALID_ARGUMENT
+    assert views(3, 4, 254, dummy) == _lib.ERR_INVALID_ARGUMENT and b"count epochs" in _lib.lib.smesh_last_error()
+    assert views(0, 4, 1, dummy) == _lib.OK                      # an empty list of views is not an error
+    assert _lib.lib.smesh_selftest_inv_sqrt(0x7F000000, 1 << 24, dummy, None) == _lib.ERR_INVALID_ARGUMENT
+    assert _lib.lib.smesh_selftest_inv_sqrt(0x3F800000, 16, None, None) == _lib.ERR_INVALID_ARGUMENT
 
 
 def test_no_cpu_fallback():
