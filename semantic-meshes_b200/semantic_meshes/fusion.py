@@ -357,8 +357,9 @@ class MeshAggregator:
 
     def add_batch(self, primitive_indices, probs, weights=None):
         """Extension: fuse B views held in batched device tensors (B,W,H) / (B,W,H,C) / (B,W,H) with one call; the same
-        result as B `add` calls in order, without B trips through Python - and with the count stage of view b+1 running
-        on a side stream under the scatter stage of view b (smesh_fuse_add_batch)."""
+        result as B `add` calls in order (up to the order of the float additions), without B trips through Python - and
+        with the views dealt to two lanes (the current stream and a side stream of the library, one counter array each),
+        so that one view's count stage, launch gaps and tail run under another view's scatter (smesh_fuse_add_batch)."""
         torch = self._torch
         ids = self._as_tensor(primitive_indices, "primitive_indices")
         pr = self._as_tensor(probs, "probs")
