@@ -16,10 +16,13 @@
 //                       (C = 2 ... 20: scatter_pair_kernel, two pixels per lane; wide C: scatter_rows_kernel, lanes across the
 //                       classes of a pixel, rows read straight from global memory)
 //   3. clear_kernel   - only in the untagged-counter mode (images of >= 2^24 pixels): zero the touched counters again
-// Inside a batch (smesh_fuse_add_batch) and for callers that hold the next index image early
-// (smesh_fuse_scatter_count_next) stage 1 of the NEXT view rides in stage 2 of this one: one more warp per CTA of the
-// ring kernels (count_job_warp) takes the next view's counts into the other of two counter arrays.
-// get() (get_kernel) stages accumulator rows through shared memory: coalesced in, one thread per row, coalesced out.
+// A batch (smesh_fuse_add_batch) deals its views to two lanes - the caller's stream and a side stream of the library, one
+// counter array each - so one view's stage 1, launch gaps and tail run under another view's stage 2. For callers that
+// hold the next index image early (smesh_fuse_scatter_count_next; also the batch when it has to stay on one stream)
+// stage 1 of the NEXT view rides in stage 2 of this one: one more warp per CTA of the ring kernels (count_job_warp)
+// takes the next view's counts into the other of two counter arrays.
+// get() (get_stream_kernel): every warp runs a two-stage bulk-copy pipeline over blocks of 32 accumulator rows - bulk
+// load, one lane per row, bulk store (get_kernel: the staged variant for very wide class vectors).
 // No tensor cores: this is an irregular gather/scatter, not a contraction.
 #include "smesh_common.cuh"
 
